@@ -3,7 +3,7 @@
 //   warp 0 (1 lane) : TMA producer   — cp.async.bulk.tensor 128B-swizzled operand tiles into a 4-stage smem ring
 //   warp 1 (1 lane) : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, 128x256x16 atoms, fp32 accumulators in TMEM
 //   warp 2          : TMEM allocator — 512 columns = two 128x256 fp32 accumulator buffers (epilogue/mainloop overlap)
-//   warps 4..7      : epilogue       — tcgen05.ld TMEM->registers, fused bias/GELU/GELU'/residual, 128-bit stores
+//   warps 4..11     : epilogue       — tcgen05.ld TMEM->regs -> swizzled smem -> coalesced fused bias/GELU/residual stores
 //
 // Operands are 16-bit (fp16 or bf16, chosen per operand in the instruction descriptor); both K-major and MN-major
 // operand storage are supported through the UMMA smem-descriptor / TMA box shapes, so the same kernel runs
@@ -31,9 +31,14 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int MN_BOX_BYTES = 64 * BK * 2;   // one [64 k][64 mn] box of an MN-major operand = 8 KiB
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 8;                        // 2 per TMEM lane quarter (each takes half of the columns)
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;   // warps 0..3: TMA / MMA / TMEM-alloc / spare
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = 1024 + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+constexpr int EPI_CHUNK = 32;                           // columns staged per step
+constexpr int EPI_WARP_BYTES = 32 * EPI_CHUNK * 4;      // 32 rows x 32 fp32, XOR-swizzled (no padding)
+constexpr int PIPE_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+constexpr int SMEM_BYTES = 1024 + PIPE_BYTES + NUM_EPI_WARPS * EPI_WARP_BYTES + 256;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct GemmKParams {
   int M, N, K;
@@ -52,128 +57,94 @@ struct GemmKParams {
   int out16_fmt, out16b_fmt, aux_fmt;
   int act;
   int skip_period;
-  int vec_ok;  // all leading dims / pointers allow 128-bit accesses
+  int vec_ok;  // all leading dims / pointers allow vector accesses on 4-column groups
   float alpha;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void store4_16(uint16_t* o, const float (&v)[4], int fmt, bool full, int ncol) {
+  if (full) {
+    uint2 w;
+    w.x = pack2_16(v[0], v[1], fmt);
+    w.y = pack2_16(v[2], v[3], fmt);
+    *reinterpret_cast<uint2*>(o) = w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < ncol) o[j] = f32_to_16(v[j], fmt);
+  }
 }
 
-// Epilogue for 8 consecutive columns of one row.
-__device__ __forceinline__ void epilogue8(const GemmKParams& p, float (&v)[8], long long row, int col, bool atomic) {
+// Epilogue for 4 consecutive columns of one row (coalesced side: 8 lanes cover 32 consecutive columns).
+// `b4` = bias for these 4 columns (already loaded), `r4` = residual (already loaded when vectorisable).
+__device__ __forceinline__ void epilogue4(const GemmKParams& p, float (&v)[4], const float4& b4, long long row, int col,
+                                          bool atomic) {
+  const int ncol = min(4, p.N - col);
+  const bool full = p.vec_ok && ncol == 4;
   if (atomic) {
     float* o = p.out32 + row * p.ld32 + col;
-    if (p.vec_ok && col + 8 <= p.N) {
-      red_add_v4(o, v[0], v[1], v[2], v[3]);
-      red_add_v4(o + 4, v[4], v[5], v[6], v[7]);
-    } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (col + j < p.N) atomicAdd(o + j, v[j]);
-    }
+    for (int j = 0; j < 4; ++j)
+      if (j < ncol) atomicAdd(o + j, v[j]);  // result unused -> RED.ADD.F32
     return;
   }
-  const bool full = p.vec_ok && (col + 8 <= p.N);
-  if (p.bias) {
-    if (full) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
-    }
-  }
+  v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
   if (p.act != ALPRO_ACT_NONE) {
     if (p.act == ALPRO_ACT_GELU || p.act == ALPRO_ACT_RELU) {
-      if (p.out16b) {  // save the pre-activation for the backward pass
-        uint16_t* o = p.out16b + row * p.ld16b + col;
-        if (full) {
-          uint4 w;
-          w.x = pack2_16(v[0], v[1], p.out16b_fmt); w.y = pack2_16(v[2], v[3], p.out16b_fmt);
-          w.z = pack2_16(v[4], v[5], p.out16b_fmt); w.w = pack2_16(v[6], v[7], p.out16b_fmt);
-          *reinterpret_cast<uint4*>(o) = w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (col + j < p.N) o[j] = f32_to_16(v[j], p.out16b_fmt);
-        }
-      }
+      if (p.out16b) store4_16(p.out16b + row * p.ld16b + col, v, p.out16b_fmt, full, ncol);
       if (p.act == ALPRO_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
       }
     } else {  // *_GRAD: multiply by f'(aux)
-      float u[8];
+      float u[4];
       const uint16_t* a = p.aux16 + row * p.ldaux + col;
       if (full) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(a));
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          u[2 * j] = f16_to_32(static_cast<uint16_t>(ww[j] & 0xffff), p.aux_fmt);
-          u[2 * j + 1] = f16_to_32(static_cast<uint16_t>(ww[j] >> 16), p.aux_fmt);
-        }
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(a));
+        u[0] = f16_to_32(static_cast<uint16_t>(w.x & 0xffff), p.aux_fmt);
+        u[1] = f16_to_32(static_cast<uint16_t>(w.x >> 16), p.aux_fmt);
+        u[2] = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), p.aux_fmt);
+        u[3] = f16_to_32(static_cast<uint16_t>(w.y >> 16), p.aux_fmt);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = (col + j < p.N) ? f16_to_32(a[j], p.aux_fmt) : 0.f;
+        for (int j = 0; j < 4; ++j) u[j] = (j < ncol) ? f16_to_32(a[j], p.aux_fmt) : 0.f;
       }
       if (p.act == ALPRO_ACT_GELU_GRAD) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(u[j]);
+        for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(u[j]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = u[j] > 0.f ? v[j] : 0.f;
+        for (int j = 0; j < 4; ++j) v[j] = u[j] > 0.f ? v[j] : 0.f;
       }
     }
   }
   if (p.resid) {
     const bool skip = p.skip_period > 0 && (row % p.skip_period) == 0;
     const float* r = p.resid + row * p.ldresid + col;
+    float rr[4];
     if (full) {
-      const float4 r0 = *reinterpret_cast<const float4*>(r);
-      const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-      if (skip) {
-        v[0] = r0.x; v[1] = r0.y; v[2] = r0.z; v[3] = r0.w; v[4] = r1.x; v[5] = r1.y; v[6] = r1.z; v[7] = r1.w;
-      } else {
-        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-      }
+      const float4 r4 = *reinterpret_cast<const float4*>(r);
+      rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (col + j < p.N) v[j] = skip ? r[j] : v[j] + r[j];
+      for (int j = 0; j < 4; ++j) rr[j] = (j < ncol) ? r[j] : 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = skip ? rr[j] : v[j] + rr[j];
   }
   if (p.out32) {
     float* o = p.out32 + row * p.ld32 + col;
     if (full) {
       *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (col + j < p.N) o[j] = v[j];
+      for (int j = 0; j < 4; ++j)
+        if (j < ncol) o[j] = v[j];
     }
   }
-  if (p.out16) {
-    uint16_t* o = p.out16 + row * p.ld16 + col;
-    if (full) {
-      uint4 w;
-      w.x = pack2_16(v[0], v[1], p.out16_fmt); w.y = pack2_16(v[2], v[3], p.out16_fmt);
-      w.z = pack2_16(v[4], v[5], p.out16_fmt); w.w = pack2_16(v[6], v[7], p.out16_fmt);
-      *reinterpret_cast<uint4*>(o) = w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (col + j < p.N) o[j] = f32_to_16(v[j], p.out16_fmt);
-    }
-  }
+  if (p.out16) store4_16(p.out16 + row * p.ld16 + col, v, p.out16_fmt, full, ncol);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -184,7 +155,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint8_t* sEpi = smem + PIPE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + NUM_EPI_WARPS * EPI_WARP_BYTES);
   uint64_t* full_bar = bars;                // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;      // [STAGES] MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;  // [2] MMA -> epilogue
@@ -205,7 +177,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -294,41 +266,68 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (TMEM lane quarter = warp % 4)
+    // ------------------------------------------------------------ epilogue
+    // TMEM lane quarter q = warp % 4 (hardware restriction); the two warps of a quarter split the 256 columns.
+    // Row-owner side: tcgen05.ld gives lane i the 32-column chunk of row q*32+i -> XOR-swizzled smem.
+    // Coalesced side: 8 lanes cover the 32 columns of one row (float4 each), 4 rows per warp instruction.
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float* stg = reinterpret_cast<float*>(sEpi + (warp - 4) * EPI_WARP_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool atomic = p.split_k > 1;
+    const int crow = lane >> 3;  // 0..3
+    const int cch = lane & 7;    // float4 index within the 32-column chunk
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int tile = w / p.split_k;
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile - m_blk * p.num_n_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const long long row = static_cast<long long>(m_blk) * BM + q * 32 + lane;
+      const long long row0 = static_cast<long long>(m_blk) * BM + q * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += EPI_CHUNK) {
         const int col0 = n_blk * BN + c;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(taddr + c, r);
         tmem_ld_wait();
-        if (row < p.M) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float v[8];
+        for (int j = 0; j < 8; ++j) {
+          float4 t = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
+                                 __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+          *reinterpret_cast<float4*>(stg + lane * EPI_CHUNK + ((j ^ (lane & 7)) << 2)) = t;
+        }
+        __syncwarp();
+        const int col = col0 + cch * 4;
+        if (col < p.N) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && !atomic) {
+            if (p.vec_ok && col + 4 <= p.N) {
+              b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            } else {
+              b4.x = __ldg(p.bias + col);
+              if (col + 1 < p.N) b4.y = __ldg(p.bias + col + 1);
+              if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
+              if (col + 3 < p.N) b4.w = __ldg(p.bias + col + 3);
+            }
+          }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
-              epilogue8(p, v, row, col, atomic);
+          for (int i = 0; i < 8; ++i) {
+            const int rl = crow + 4 * i;
+            const long long row = row0 + rl;
+            if (row < p.M) {
+              const float4 t = *reinterpret_cast<const float4*>(stg + rl * EPI_CHUNK + ((cch ^ (rl & 7)) << 2));
+              float v[4] = {t.x, t.y, t.z, t.w};
+              epilogue4(p, v, b4, row, col, atomic);
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -444,9 +443,9 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   if (p.bias) vec = vec && aligned16(p.bias);
   if (p.out32) vec = vec && aligned16(p.out32) && (p.ld32 % 4) == 0;
   if (p.resid) vec = vec && aligned16(p.resid) && (p.ldresid % 4) == 0;
-  if (p.out16) vec = vec && aligned16(p.out16) && (p.ld16 % 8) == 0;
-  if (p.out16b) vec = vec && aligned16(p.out16b) && (p.ld16b % 8) == 0;
-  if (p.aux16) vec = vec && aligned16(p.aux16) && (p.ldaux % 8) == 0;
+  if (p.out16) vec = vec && aligned16(p.out16) && (p.ld16 % 4) == 0;
+  if (p.out16b) vec = vec && aligned16(p.out16b) && (p.ld16b % 4) == 0;
+  if (p.aux16) vec = vec && aligned16(p.aux16) && (p.ldaux % 4) == 0;
   p.vec_ok = vec ? 1 : 0;
 
   CUtensorMap tmA, tmB;

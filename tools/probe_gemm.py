@@ -17,21 +17,21 @@ CASES = {
     "nt_multi": (1024, 768, 768, 0, 0, "f16", "f16", {}),
     "nt_tails": (200, 296, 104, 0, 0, "f16", "f16", {}),
     "nt_bf16": (512, 512, 256, 0, 0, "bf16", "bf16", {}),
-    "nt_mixed": (512, 512, 256, 0, 0, "bf16", "f16", {}),
-    "nt_bias_gelu": (640, 3072, 768, 0, 0, "f16", "f16", {"bias": 1, "act": 1, "out16b": 1}),
+        "nt_bias_gelu": (640, 3072, 768, 0, 0, "f16", "f16", {"bias": 1, "act": 1, "out16b": 1}),
     "nt_resid_skip": (3 * 17, 768, 768, 0, 0, "f16", "f16", {"bias": 1, "resid": 1, "skip": 17, "out32": 1}),
     "nn_dgrad": (1024, 768, 2304, 0, 1, "bf16", "bf16", {}),
-    "nn_dgrad_mixed_gelugrad": (640, 768, 3072, 0, 1, "bf16", "f16", {"act": 2}),
+    "nn_dgrad_gelugrad": (640, 768, 3072, 0, 1, "f16", "f16", {"act": 2}),
     "nn_tails": (200, 296, 104, 0, 1, "f16", "f16", {}),
     "tn_wgrad": (2304, 768, 4096, 1, 1, "bf16", "bf16", {"split": -1}),
-    "tn_wgrad_mixed": (768, 3072, 5000, 1, 1, "bf16", "f16", {"split": -1}),
+    "tn_wgrad_f16": (768, 3072, 5000, 1, 1, "f16", "f16", {"split": -1}),
     "tn_nosplit": (256, 512, 1000, 1, 1, "f16", "f16", {"out32": 1}),
     "tk_amn_bk": (256, 512, 1000, 1, 0, "f16", "f16", {"out32": 1}),
     "nt_vocab_unaligned": (1280, 30522, 768, 0, 0, "f16", "f16", {"bias": 1, "out32": 1}),
     "perf_qkv": (50176, 2304, 768, 0, 0, "f16", "f16", {"bias": 1, "perf": 1}),
     "perf_fc2": (50208, 768, 3072, 0, 0, "f16", "f16", {"bias": 1, "resid": 1, "out32": 1, "perf": 1}),
-    "perf_wgrad": (2304, 768, 50176, 1, 1, "bf16", "f16", {"split": -1, "perf": 1}),
-    "perf_dgrad": (50176, 768, 2304, 0, 1, "bf16", "f16", {"perf": 1}),
+    "perf_wgrad": (2304, 768, 50176, 1, 1, "f16", "f16", {"split": -1, "perf": 1}),
+    "perf_fc1_gelu": (50208, 3072, 768, 0, 0, "f16", "f16", {"bias": 1, "act": 1, "out16b": 1, "perf": 1}),
+    "perf_dgrad": (50176, 768, 2304, 0, 1, "f16", "f16", {"perf": 1}),
 }
 
 
