@@ -1,0 +1,721 @@
+// Attention kernels of the ALPRO path (head_dim = 64).
+//
+//  * temporal attention (TimeSformer divided attention over the T frames of one patch position, T <= 8):
+//    one warp per (clip, patch, head); the whole TxT problem lives in registers. Reference: Attention.forward
+//    vit.py:81-100 called through Block.forward vit.py:146-157 on '(b h w) t m'.
+//  * sequence attention for S <= 256 keys (TimeSformer spatial attention over cls + N patches of one frame,
+//    BERT text / fusion self-attention with additive key mask): one CTA per (sequence, head), Q/K/V tiles in
+//    XOR-swizzled shared memory, QK^T and PV on mma.sync m16n8k16 tensor-core atoms with fp32 softmax.
+//    Reference: vit.py:81-100 via Block.forward vit.py:165-181; BertSelfAttention.forward xbert.py:263-346.
+//    Token gathering for the '(b t) (h w)' view is done by index arithmetic on the canonical 'b (h w t)' layout
+//    instead of the reference's rearrange/cat copies.
+//
+// Backward kernels recompute the probabilities from the saved log-sum-exp (no SxS tensor ever reaches HBM).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace alpro {
+namespace {
+
+constexpr int DH = 64;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ================================================================================================ temporal attention
+struct TAttnParams {
+  const uint16_t* qkv;  // [rows, 3*d]
+  uint16_t* out;        // fwd: o [rows, d];  bwd: dqkv [rows, 3*d]
+  const uint16_t* dout; // bwd: do [rows, d]
+  long long ld_qkv, ld_out, ld_dout;
+  int B, N, heads, d, fmt;
+  float scale;
+};
+
+template <int T>
+__device__ __forceinline__ void tattn_load(const TAttnParams& p, long long row0, int head, int lane, float (&q)[T][2],
+                                           float (&k)[T][2], float (&v)[T][2]) {
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const uint16_t* base = p.qkv + (row0 + t) * p.ld_qkv + head * DH + lane * 2;
+    const uint32_t wq = *reinterpret_cast<const uint32_t*>(base);
+    const uint32_t wk = *reinterpret_cast<const uint32_t*>(base + p.d);
+    const uint32_t wv = *reinterpret_cast<const uint32_t*>(base + 2 * p.d);
+    q[t][0] = f16_to_32(wq & 0xffff, p.fmt); q[t][1] = f16_to_32(wq >> 16, p.fmt);
+    k[t][0] = f16_to_32(wk & 0xffff, p.fmt); k[t][1] = f16_to_32(wk >> 16, p.fmt);
+    v[t][0] = f16_to_32(wv & 0xffff, p.fmt); v[t][1] = f16_to_32(wv >> 16, p.fmt);
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void tattn_probs(const float (&q)[T][2], const float (&k)[T][2], float scale,
+                                            float (&pr)[T][T]) {
+#pragma unroll
+  for (int i = 0; i < T; ++i) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      pr[i][j] = warp_sum(q[i][0] * k[j][0] + q[i][1] * k[j][1]) * scale;
+      mx = fmaxf(mx, pr[i][j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      pr[i][j] = __expf(pr[i][j] - mx);
+      sum += pr[i][j];
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < T; ++j) pr[i][j] *= inv;
+  }
+}
+
+// grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by warp (n==0,head).
+template <int T>
+__global__ void tattn_fwd_kernel(const TAttnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = static_cast<long long>(p.B) * p.N * p.heads;
+  if (unit >= total) return;
+  const int head = static_cast<int>(unit % p.heads);
+  const long long bn = unit / p.heads;
+  const int n = static_cast<int>(bn % p.N);
+  const long long b = bn / p.N;
+  const long long clip_rows = 1 + static_cast<long long>(p.N) * T;
+  const long long row0 = b * clip_rows + 1 + static_cast<long long>(n) * T;
+  if (n == 0) *reinterpret_cast<uint32_t*>(p.out + b * clip_rows * p.ld_out + head * DH + lane * 2) = 0u;  // cls row
+  float q[T][2], k[T][2], v[T][2], pr[T][T];
+  tattn_load<T>(p, row0, head, lane, q, k, v);
+  tattn_probs<T>(q, k, p.scale, pr);
+#pragma unroll
+  for (int i = 0; i < T; ++i) {
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      o0 += pr[i][j] * v[j][0];
+      o1 += pr[i][j] * v[j][1];
+    }
+    *reinterpret_cast<uint32_t*>(p.out + (row0 + i) * p.ld_out + head * DH + lane * 2) = pack2_16(o0, o1, p.fmt);
+  }
+}
+
+template <int T>
+__global__ void tattn_bwd_kernel(const TAttnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = static_cast<long long>(p.B) * p.N * p.heads;
+  if (unit >= total) return;
+  const int head = static_cast<int>(unit % p.heads);
+  const long long bn = unit / p.heads;
+  const int n = static_cast<int>(bn % p.N);
+  const long long b = bn / p.N;
+  const long long clip_rows = 1 + static_cast<long long>(p.N) * T;
+  const long long row0 = b * clip_rows + 1 + static_cast<long long>(n) * T;
+  if (n == 0) {  // cls row receives no gradient from the temporal branch
+    uint16_t* z = p.out + b * clip_rows * p.ld_out + head * DH + lane * 2;
+    *reinterpret_cast<uint32_t*>(z) = 0u;
+    *reinterpret_cast<uint32_t*>(z + p.d) = 0u;
+    *reinterpret_cast<uint32_t*>(z + 2 * p.d) = 0u;
+  }
+  float q[T][2], k[T][2], v[T][2], pr[T][T], go[T][2];
+  tattn_load<T>(p, row0, head, lane, q, k, v);
+  tattn_probs<T>(q, k, p.scale, pr);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p.dout + (row0 + t) * p.ld_dout + head * DH + lane * 2);
+    go[t][0] = f16_to_32(w & 0xffff, p.fmt);
+    go[t][1] = f16_to_32(w >> 16, p.fmt);
+  }
+  float dq[T][2], dk[T][2], dv[T][2];
+#pragma unroll
+  for (int t = 0; t < T; ++t) dq[t][0] = dq[t][1] = dk[t][0] = dk[t][1] = dv[t][0] = dv[t][1] = 0.f;
+#pragma unroll
+  for (int i = 0; i < T; ++i) {
+    float dp[T];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      dp[j] = warp_sum(go[i][0] * v[j][0] + go[i][1] * v[j][1]);
+      dot += dp[j] * pr[i][j];
+      dv[j][0] += pr[i][j] * go[i][0];
+      dv[j][1] += pr[i][j] * go[i][1];
+    }
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      const float ds = pr[i][j] * (dp[j] - dot) * p.scale;
+      dq[i][0] += ds * k[j][0]; dq[i][1] += ds * k[j][1];
+      dk[j][0] += ds * q[i][0]; dk[j][1] += ds * q[i][1];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    uint16_t* o = p.out + (row0 + t) * p.ld_out + head * DH + lane * 2;
+    *reinterpret_cast<uint32_t*>(o) = pack2_16(dq[t][0], dq[t][1], p.fmt);
+    *reinterpret_cast<uint32_t*>(o + p.d) = pack2_16(dk[t][0], dk[t][1], p.fmt);
+    *reinterpret_cast<uint32_t*>(o + 2 * p.d) = pack2_16(dv[t][0], dv[t][1], p.fmt);
+  }
+}
+
+// ================================================================================================ sequence attention
+struct SAttnParams {
+  const uint16_t* qkv;   // [rows, ld_qkv]: q at col 0, k at col d, v at col 2d (head h at +h*64)
+  const float* mask;     // additive key mask [nseq, S] or null
+  uint16_t* o;           // fwd out [rows, ld_o]
+  uint16_t* cls_o;       // fwd: if non-null, token 0 output goes to cls_o[seq, d] instead of its canonical row
+  float* lse;            // [nseq, heads, S]
+  // backward
+  const uint16_t* dout;  // [rows, ld_o] upstream grad; with seq_div > 1 token 0 is the group's shared cls row whose
+                         // forward value was the mean over the seq_div frames, so each frame receives dout / seq_div
+  uint16_t* dqkv;        // [rows, ld_qkv]
+  float* dcls_qkv;       // [nseq, 3*d] fp32: per-sequence gradient of the shared cls q/k/v row (when seq_div > 1)
+  long long ld_qkv, ld_o;
+  int S, nseq, heads, d, fmt;
+  int seq_div, stride;   // row(seq, j) = (seq / seq_div) * clip_rows + (j == 0 ? 0 : 1 + seq % seq_div + (j-1) * stride)
+  long long clip_rows;
+  float scale;
+};
+
+__device__ __forceinline__ long long srow(const SAttnParams& p, int seq, int j) {
+  const long long base = static_cast<long long>(seq / p.seq_div) * p.clip_rows;
+  return j == 0 ? base : base + 1 + (seq % p.seq_div) + static_cast<long long>(j - 1) * p.stride;
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <bool BF>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (BF) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+template <bool BF>
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return pack2_16(a, b, BF ? 1 : 0); }
+
+// smem tile [rows][64] 16-bit, 128-byte rows, 16-byte chunk index XOR (row & 7)
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int col) {
+  return base + row * 128 + ((((col >> 3) ^ (row & 7)) << 4)) + ((col & 7) << 1);
+}
+
+// Cooperative gather of one [S_pad][64] tile (which: 0=q,1=k,2=v of qkv; or a plain [rows, ld] matrix with col offset).
+__device__ __forceinline__ void load_tile(const SAttnParams& p, const uint16_t* src, long long ld, int col0, int seq,
+                                          int S_pad, uint8_t* smem_tile, const uint16_t* tok0_override) {
+  for (int idx = threadIdx.x; idx < S_pad * 8; idx += blockDim.x) {
+    const int row = idx >> 3, ch = idx & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < p.S) {
+      const uint16_t* g = (row == 0 && tok0_override) ? tok0_override + ch * 8
+                                                       : src + srow(p, seq, row) * ld + col0 + ch * 8;
+      v = *reinterpret_cast<const uint4*>(g);
+    }
+    *reinterpret_cast<uint4*>(smem_tile + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// grid (heads, nseq), 128 threads. NT_MAX = max number of 8-key tiles (S_pad / 8).
+template <bool BF, int NT_MAX>
+__global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int S_pad = (p.S + 15) & ~15;
+  uint8_t* sQ = sm;
+  uint8_t* sK = sQ + S_pad * 128;
+  uint8_t* sV = sK + S_pad * 128;
+  float* sMask = reinterpret_cast<float*>(sV + S_pad * 128);
+  load_tile(p, p.qkv, p.ld_qkv, head * DH, seq, S_pad, sQ, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, seq, S_pad, sK, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S_pad, sV, nullptr);
+  for (int j = threadIdx.x; j < S_pad; j += blockDim.x)
+    sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV);
+  const int nt = S_pad >> 3;
+  const float sl2 = p.scale * LOG2E;
+
+  for (int qt = warp; qt < (S_pad >> 4); qt += 4) {
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldsm_x4(qa[ks], tile_addr(q_base, qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 16 + (lane >> 4) * 8));
+    float s[NT_MAX][4];
+#pragma unroll
+    for (int n2 = 0; n2 < NT_MAX / 2; ++n2) {
+      if (n2 * 2 < nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[2 * n2][e] = s[2 * n2 + 1][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t kb[4];
+          ldsm_x4(kb, tile_addr(k_base, n2 * 16 + (lane & 7) + (lane >> 4) * 8, ks * 16 + ((lane >> 3) & 1) * 8));
+          mma16816<BF>(s[2 * n2], qa[ks], kb[0], kb[1]);
+          mma16816<BF>(s[2 * n2 + 1], qa[ks], kb[2], kb[3]);
+        }
+      }
+    }
+    // softmax over keys (rows g and g+8 of this query tile), base-2 domain
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT_MAX; ++n) {
+      if (n < nt) {
+        const float mk0 = sMask[n * 8 + 2 * t], mk1 = sMask[n * 8 + 2 * t + 1];
+        s[n][0] = s[n][0] * sl2 + mk0; s[n][1] = s[n][1] * sl2 + mk1;
+        s[n][2] = s[n][2] * sl2 + mk0; s[n][3] = s[n][3] * sl2 + mk1;
+        m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+        m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT_MAX; ++n) {
+      if (n < nt) {
+        s[n][0] = exp2f(s[n][0] - m0); s[n][1] = exp2f(s[n][1] - m0);
+        s[n][2] = exp2f(s[n][2] - m1); s[n][3] = exp2f(s[n][3] - m1);
+        l0 += s[n][0] + s[n][1];
+        l1 += s[n][2] + s[n][3];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // O = P V
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT_MAX / 2; ++kk) {
+      if (kk * 2 < nt) {
+        uint32_t pa[4];
+        pa[0] = pack2<BF>(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack2<BF>(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack2<BF>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack2<BF>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t vb[4];
+          ldsm_x4_t(vb, tile_addr(v_base, kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 16 + (lane >> 4) * 8));
+          mma16816<BF>(o[2 * dp], pa, vb[0], vb[1]);
+          mma16816<BF>(o[2 * dp + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = qt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = half ? r1 : r0;
+      if (r < p.S) {
+        const float inv = half ? i1 : i0;
+        uint16_t* dst = (r == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
+                                            : p.o + srow(p, seq, r) * p.ld_o + head * DH;
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+          *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * t) =
+              pack2<BF>(o[n][half * 2] * inv, o[n][half * 2 + 1] * inv);
+        if (t == 0 && p.lse)
+          p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + r] = ((half ? m1 : m0) + log2f(half ? l1 : l0));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// grid (heads, nseq), 128 threads. smem: Q, K, V, dO tiles + lse2[S_pad] (base-2 log-sum-exp) + D[S_pad] + mask.
+// Phase A: each warp owns 16-query tiles -> dQ.   Phase B: each warp owns 16-key tiles -> dK, dV (recomputing S^T).
+template <bool BF>
+__global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int S_pad = (p.S + 15) & ~15;
+  uint8_t* sQ = sm;
+  uint8_t* sK = sQ + S_pad * 128;
+  uint8_t* sV = sK + S_pad * 128;
+  uint8_t* sG = sV + S_pad * 128;  // dO
+  float* sMask = reinterpret_cast<float*>(sG + S_pad * 128);
+  float* sLse = sMask + S_pad;
+  float* sD = sLse + S_pad;
+  load_tile(p, p.qkv, p.ld_qkv, head * DH, seq, S_pad, sQ, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, seq, S_pad, sK, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S_pad, sV, nullptr);
+  load_tile(p, p.dout, p.ld_o, head * DH, seq, S_pad, sG, nullptr);
+  const float gscale0 = 1.f / p.seq_div;  // d(mean_t cls_t) / d cls_t
+  for (int j = threadIdx.x; j < S_pad; j += blockDim.x) {
+    sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
+    sLse[j] = j < p.S ? p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + j] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // token-0 upstream gradient scaling (mean over frames) applied in place, then D = rowsum(dO * O) recomputed as
+  // sum_j P_ij dP_ij is avoided: O is not stored per frame for the cls row, so D is computed from P and dP below.
+  if (p.seq_div > 1 && warp == 0) {
+    // scale row 0 of dO by 1/seq_div
+    for (int c = lane; c < 64; c += 32) {
+      uint16_t* e = reinterpret_cast<uint16_t*>(sG + 0 * 128 + ((((c >> 3) ^ 0) << 4)) + ((c & 7) << 1));
+      *e = f32_to_16(f16_to_32(*e, BF ? 1 : 0) * gscale0, BF ? 1 : 0);
+    }
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV), g_base = smem_u32(sG);
+  const float sl2 = p.scale * LOG2E;
+  const int nkb = S_pad >> 4;  // 16-wide blocks along either sequence axis
+
+  // ---------------- pass 0: D_i = sum_j P_ij * dP_ij (per query row), warp per query tile
+  for (int qt = warp; qt < nkb; qt += 4) {
+    uint32_t qa[4][4], ga[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int row = qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
+      ldsm_x4(qa[ks], tile_addr(q_base, row, col));
+      ldsm_x4(ga[ks], tile_addr(g_base, row, col));
+    }
+    const float ls0 = sLse[qt * 16 + g], ls1 = sLse[qt * 16 + g + 8];
+    float d0 = 0.f, d1 = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t kf[4], vf[4];
+        const int row = kb * 16 + (lane & 7) + (lane >> 4) * 8, col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kf, tile_addr(k_base, row, col));
+        ldsm_x4(vf, tile_addr(v_base, row, col));
+        mma16816<BF>(s[0], qa[ks], kf[0], kf[1]);
+        mma16816<BF>(s[1], qa[ks], kf[2], kf[3]);
+        mma16816<BF>(dp[0], ga[ks], vf[0], vf[1]);
+        mma16816<BF>(dp[1], ga[ks], vf[2], vf[3]);
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const float mk0 = sMask[kb * 16 + n * 8 + 2 * t], mk1 = sMask[kb * 16 + n * 8 + 2 * t + 1];
+        d0 += exp2f(s[n][0] * sl2 + mk0 - ls0) * dp[n][0] + exp2f(s[n][1] * sl2 + mk1 - ls0) * dp[n][1];
+        d1 += exp2f(s[n][2] * sl2 + mk0 - ls1) * dp[n][2] + exp2f(s[n][3] * sl2 + mk1 - ls1) * dp[n][3];
+      }
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    if (t == 0) {
+      sD[qt * 16 + g] = d0;
+      sD[qt * 16 + g + 8] = d1;
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase A: dQ (warp per 16-query tile)
+  for (int qt = warp; qt < nkb; qt += 4) {
+    uint32_t qa[4][4], ga[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int row = qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
+      ldsm_x4(qa[ks], tile_addr(q_base, row, col));
+      ldsm_x4(ga[ks], tile_addr(g_base, row, col));
+    }
+    const float ls0 = sLse[qt * 16 + g], ls1 = sLse[qt * 16 + g + 8];
+    const float D0 = sD[qt * 16 + g], D1 = sD[qt * 16 + g + 8];
+    float dq[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dq[n][e] = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t kf[4], vf[4];
+        const int row = kb * 16 + (lane & 7) + (lane >> 4) * 8, col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kf, tile_addr(k_base, row, col));
+        ldsm_x4(vf, tile_addr(v_base, row, col));
+        mma16816<BF>(s[0], qa[ks], kf[0], kf[1]);
+        mma16816<BF>(s[1], qa[ks], kf[2], kf[3]);
+        mma16816<BF>(dp[0], ga[ks], vf[0], vf[1]);
+        mma16816<BF>(dp[1], ga[ks], vf[2], vf[3]);
+      }
+      float ds[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const float mk0 = sMask[kb * 16 + n * 8 + 2 * t], mk1 = sMask[kb * 16 + n * 8 + 2 * t + 1];
+        ds[n][0] = exp2f(s[n][0] * sl2 + mk0 - ls0) * (dp[n][0] - D0) * p.scale;
+        ds[n][1] = exp2f(s[n][1] * sl2 + mk1 - ls0) * (dp[n][1] - D0) * p.scale;
+        ds[n][2] = exp2f(s[n][2] * sl2 + mk0 - ls1) * (dp[n][2] - D1) * p.scale;
+        ds[n][3] = exp2f(s[n][3] * sl2 + mk1 - ls1) * (dp[n][3] - D1) * p.scale;
+      }
+      uint32_t da[4] = {pack2<BF>(ds[0][0], ds[0][1]), pack2<BF>(ds[0][2], ds[0][3]), pack2<BF>(ds[1][0], ds[1][1]),
+                        pack2<BF>(ds[1][2], ds[1][3])};
+#pragma unroll
+      for (int dpair = 0; dpair < 4; ++dpair) {  // dQ += dS K   (B = K[key][dh], k = key -> transposed ldmatrix)
+        uint32_t kb4[4];
+        ldsm_x4_t(kb4, tile_addr(k_base, kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dpair * 16 + (lane >> 4) * 8));
+        mma16816<BF>(dq[2 * dpair], da, kb4[0], kb4[1]);
+        mma16816<BF>(dq[2 * dpair + 1], da, kb4[2], kb4[3]);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = qt * 16 + g + half * 8;
+      if (r < p.S) {
+        if (r == 0 && p.dcls_qkv) {
+          float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + head * DH;
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            dst[n * 8 + 2 * t] = dq[n][half * 2];
+            dst[n * 8 + 2 * t + 1] = dq[n][half * 2 + 1];
+          }
+        } else {
+          uint16_t* dst = p.dqkv + srow(p, seq, r) * p.ld_qkv + head * DH;
+#pragma unroll
+          for (int n = 0; n < 8; ++n)
+            *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * t) = pack2<BF>(dq[n][half * 2], dq[n][half * 2 + 1]);
+        }
+      }
+    }
+  }
+
+  // ---------------- phase B: dK, dV (warp per 16-key tile); S^T = K Q^T, dP^T = V dO^T
+  for (int kt = warp; kt < nkb; kt += 4) {
+    uint32_t ka[4][4], va[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
+      ldsm_x4(ka[ks], tile_addr(k_base, row, col));
+      ldsm_x4(va[ks], tile_addr(v_base, row, col));
+    }
+    const float mk0 = sMask[kt * 16 + g], mk1 = sMask[kt * 16 + g + 8];  // key = fragment row now
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dk[n][e] = dv[n][e] = 0.f;
+    for (int qb = 0; qb < nkb; ++qb) {
+      float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t qf[4], gf[4];
+        const int row = qb * 16 + (lane & 7) + (lane >> 4) * 8, col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(qf, tile_addr(q_base, row, col));
+        ldsm_x4(gf, tile_addr(g_base, row, col));
+        mma16816<BF>(st[0], ka[ks], qf[0], qf[1]);
+        mma16816<BF>(st[1], ka[ks], qf[2], qf[3]);
+        mma16816<BF>(dpt[0], va[ks], gf[0], gf[1]);
+        mma16816<BF>(dpt[1], va[ks], gf[2], gf[3]);
+      }
+      float pt[2][4], dst_[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int qc = qb * 16 + n * 8 + 2 * t;  // query index = fragment column
+        const float l0 = sLse[qc], l1 = sLse[qc + 1], D0 = sD[qc], D1 = sD[qc + 1];
+        const bool v0 = qc < p.S, v1 = qc + 1 < p.S;  // padded query rows contribute nothing
+        pt[n][0] = v0 ? exp2f(st[n][0] * sl2 + mk0 - l0) : 0.f;
+        pt[n][1] = v1 ? exp2f(st[n][1] * sl2 + mk0 - l1) : 0.f;
+        pt[n][2] = v0 ? exp2f(st[n][2] * sl2 + mk1 - l0) : 0.f;
+        pt[n][3] = v1 ? exp2f(st[n][3] * sl2 + mk1 - l1) : 0.f;
+        dst_[n][0] = pt[n][0] * (dpt[n][0] - D0) * p.scale;
+        dst_[n][1] = pt[n][1] * (dpt[n][1] - D1) * p.scale;
+        dst_[n][2] = pt[n][2] * (dpt[n][2] - D0) * p.scale;
+        dst_[n][3] = pt[n][3] * (dpt[n][3] - D1) * p.scale;
+      }
+      uint32_t pa[4] = {pack2<BF>(pt[0][0], pt[0][1]), pack2<BF>(pt[0][2], pt[0][3]), pack2<BF>(pt[1][0], pt[1][1]),
+                        pack2<BF>(pt[1][2], pt[1][3])};
+      uint32_t da[4] = {pack2<BF>(dst_[0][0], dst_[0][1]), pack2<BF>(dst_[0][2], dst_[0][3]),
+                        pack2<BF>(dst_[1][0], dst_[1][1]), pack2<BF>(dst_[1][2], dst_[1][3])};
+#pragma unroll
+      for (int dpair = 0; dpair < 4; ++dpair) {
+        uint32_t gb[4], qb4[4];
+        const uint32_t off_row = qb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, off_col = dpair * 16 + (lane >> 4) * 8;
+        ldsm_x4_t(gb, tile_addr(g_base, off_row, off_col));   // dV += P^T dO
+        ldsm_x4_t(qb4, tile_addr(q_base, off_row, off_col));  // dK += dS^T Q
+        mma16816<BF>(dv[2 * dpair], pa, gb[0], gb[1]);
+        mma16816<BF>(dv[2 * dpair + 1], pa, gb[2], gb[3]);
+        mma16816<BF>(dk[2 * dpair], da, qb4[0], qb4[1]);
+        mma16816<BF>(dk[2 * dpair + 1], da, qb4[2], qb4[3]);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = kt * 16 + g + half * 8;
+      if (r < p.S) {
+        if (r == 0 && p.dcls_qkv) {
+          float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + head * DH;
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            dst[p.d + n * 8 + 2 * t] = dk[n][half * 2];
+            dst[p.d + n * 8 + 2 * t + 1] = dk[n][half * 2 + 1];
+            dst[2 * p.d + n * 8 + 2 * t] = dv[n][half * 2];
+            dst[2 * p.d + n * 8 + 2 * t + 1] = dv[n][half * 2 + 1];
+          }
+        } else {
+          uint16_t* dst = p.dqkv + srow(p, seq, r) * p.ld_qkv + head * DH;
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            *reinterpret_cast<uint32_t*>(dst + p.d + n * 8 + 2 * t) = pack2<BF>(dk[n][half * 2], dk[n][half * 2 + 1]);
+            *reinterpret_cast<uint32_t*>(dst + 2 * p.d + n * 8 + 2 * t) = pack2<BF>(dv[n][half * 2], dv[n][half * 2 + 1]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// dqkv[group cls row] = sum over the group's seq_div frames of the per-sequence cls-row gradients
+__global__ void cls_qkv_reduce_kernel(const float* __restrict__ part, uint16_t* __restrict__ dqkv, long long ld,
+                                      long long clip_rows, int groups, int seq_div, int d3, int fmt) {
+  const long long total = static_cast<long long>(groups) * d3;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int gidx = static_cast<int>(i / d3);
+    const int c = static_cast<int>(i - static_cast<long long>(gidx) * d3);
+    float s = 0.f;
+    for (int t = 0; t < seq_div; ++t) s += part[(static_cast<long long>(gidx) * seq_div + t) * d3 + c];
+    dqkv[gidx * clip_rows * ld + c] = f32_to_16(s, fmt);
+  }
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(%zu bytes): %s", bytes, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace alpro
+
+using namespace alpro;
+
+extern "C" int alpro_temporal_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int B, int N, int T,
+                                       int heads, int fmt, float scale, void* stream) {
+  ALPRO_REQUIRE(qkv && out && B > 0 && N > 0 && heads > 0, "alpro_temporal_attn_fwd: bad args");
+  TAttnParams p{};
+  p.qkv = static_cast<const uint16_t*>(qkv); p.out = static_cast<uint16_t*>(out);
+  p.ld_qkv = ld_qkv; p.ld_out = ld_out; p.B = B; p.N = N; p.heads = heads; p.d = heads * DH; p.fmt = fmt; p.scale = scale;
+  const long long units = static_cast<long long>(B) * N * heads;
+  const int wpb = 4;
+  const unsigned grid = static_cast<unsigned>(cdiv(units, wpb));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (T) {
+    case 1: tattn_fwd_kernel<1><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 2: tattn_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 4: tattn_fwd_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 8: tattn_fwd_kernel<8><<<grid, wpb * 32, 0, st>>>(p); break;
+    default: set_last_error("alpro_temporal_attn_fwd: T=%d unsupported (1,2,4,8)", T); return ALPRO_ENOTSUP;
+  }
+  ALPRO_CHECK_LAUNCH("alpro_temporal_attn_fwd");
+  return 0;
+}
+
+extern "C" int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const void* dout, int64_t ld_dout, void* dqkv,
+                                       int64_t ld_dqkv, int B, int N, int T, int heads, int fmt, float scale,
+                                       void* stream) {
+  ALPRO_REQUIRE(qkv && dout && dqkv, "alpro_temporal_attn_bwd: bad args");
+  TAttnParams p{};
+  p.qkv = static_cast<const uint16_t*>(qkv); p.out = static_cast<uint16_t*>(dqkv);
+  p.dout = static_cast<const uint16_t*>(dout);
+  p.ld_qkv = ld_qkv; p.ld_out = ld_dqkv; p.ld_dout = ld_dout;
+  p.B = B; p.N = N; p.heads = heads; p.d = heads * DH; p.fmt = fmt; p.scale = scale;
+  const long long units = static_cast<long long>(B) * N * heads;
+  const int wpb = 4;
+  const unsigned grid = static_cast<unsigned>(cdiv(units, wpb));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (T) {
+    case 1: tattn_bwd_kernel<1><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 2: tattn_bwd_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 4: tattn_bwd_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 8: tattn_bwd_kernel<8><<<grid, wpb * 32, 0, st>>>(p); break;
+    default: set_last_error("alpro_temporal_attn_bwd: T=%d unsupported (1,2,4,8)", T); return ALPRO_ENOTSUP;
+  }
+  ALPRO_CHECK_LAUNCH("alpro_temporal_attn_bwd");
+  return 0;
+}
+
+static int fill_sattn(SAttnParams& p, const void* qkv, int64_t ld_qkv, const float* mask, int S, int nseq, int heads,
+                      int fmt, int seq_div, int stride, int64_t clip_rows, float scale) {
+  ALPRO_REQUIRE(qkv && S > 0 && S <= 256 && nseq > 0 && heads > 0, "alpro_seq_attn: bad args (S=%d must be <= 256)", S);
+  ALPRO_REQUIRE(seq_div >= 1 && stride >= 1 && (ld_qkv % 8) == 0, "alpro_seq_attn: bad layout");
+  p.qkv = static_cast<const uint16_t*>(qkv); p.ld_qkv = ld_qkv; p.mask = mask; p.S = S; p.nseq = nseq; p.heads = heads;
+  p.d = heads * DH; p.fmt = fmt; p.seq_div = seq_div; p.stride = stride; p.clip_rows = clip_rows; p.scale = scale;
+  return 0;
+}
+
+extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* mask, void* o, int64_t ld_o,
+                                  void* cls_o, float* lse, int S, int nseq, int heads, int fmt, int seq_div, int stride,
+                                  int64_t clip_rows, float scale, void* stream) {
+  SAttnParams p{};
+  int rc = fill_sattn(p, qkv, ld_qkv, mask, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale);
+  if (rc) return rc;
+  ALPRO_REQUIRE(o && (ld_o % 8) == 0, "alpro_seq_attn_fwd: bad output");
+  p.o = static_cast<uint16_t*>(o); p.ld_o = ld_o; p.cls_o = static_cast<uint16_t*>(cls_o); p.lse = lse;
+  const int S_pad = (S + 15) & ~15;
+  const size_t smem = static_cast<size_t>(S_pad) * 128 * 3 + S_pad * sizeof(float);
+  dim3 grid(heads, nseq);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LAUNCH_FWD(BF, NT)                                                   \
+  do {                                                                       \
+    rc = set_smem(sattn_fwd_kernel<BF, NT>, smem);                           \
+    if (rc) return rc;                                                       \
+    sattn_fwd_kernel<BF, NT><<<grid, 128, smem, st>>>(p);                    \
+  } while (0)
+  if (fmt == 1) {
+    if (S_pad <= 64) LAUNCH_FWD(true, 8); else if (S_pad <= 128) LAUNCH_FWD(true, 16); else LAUNCH_FWD(true, 32);
+  } else {
+    if (S_pad <= 64) LAUNCH_FWD(false, 8); else if (S_pad <= 128) LAUNCH_FWD(false, 16); else LAUNCH_FWD(false, 32);
+  }
+#undef LAUNCH_FWD
+  ALPRO_CHECK_LAUNCH("alpro_seq_attn_fwd");
+  return 0;
+}
+
+extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* dout,
+                                  int64_t ld_o, void* dqkv, float* dcls_qkv_scratch, int S, int nseq,
+                                  int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
+                                  void* stream) {
+  SAttnParams p{};
+  int rc = fill_sattn(p, qkv, ld_qkv, mask, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale);
+  if (rc) return rc;
+  ALPRO_REQUIRE(lse && dout && dqkv && (ld_o % 8) == 0, "alpro_seq_attn_bwd: bad args");
+  ALPRO_REQUIRE(seq_div == 1 || dcls_qkv_scratch, "alpro_seq_attn_bwd: shared-cls layout needs the fp32 scratch");
+  p.lse = const_cast<float*>(lse); p.dout = static_cast<const uint16_t*>(dout); p.ld_o = ld_o;
+  p.dqkv = static_cast<uint16_t*>(dqkv);
+  p.dcls_qkv = seq_div > 1 ? dcls_qkv_scratch : nullptr;
+  const int S_pad = (S + 15) & ~15;
+  const size_t smem = static_cast<size_t>(S_pad) * 128 * 4 + 3 * S_pad * sizeof(float);
+  dim3 grid(heads, nseq);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (fmt == 1) {
+    rc = set_smem(sattn_bwd_kernel<true>, smem);
+    if (rc) return rc;
+    sattn_bwd_kernel<true><<<grid, 128, smem, st>>>(p);
+  } else {
+    rc = set_smem(sattn_bwd_kernel<false>, smem);
+    if (rc) return rc;
+    sattn_bwd_kernel<false><<<grid, 128, smem, st>>>(p);
+  }
+  ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd");
+  if (seq_div > 1) {
+    const int groups = nseq / seq_div;
+    const long long total = static_cast<long long>(groups) * 3 * p.d;
+    long long g = cdiv(total, 256);
+    cls_qkv_reduce_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(dcls_qkv_scratch, p.dqkv, ld_qkv, clip_rows, groups,
+                                                                    seq_div, 3 * p.d, fmt);
+    ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd(cls reduce)");
+  }
+  return 0;
+}

@@ -1,0 +1,624 @@
+// HBM-bound kernels of the ALPRO path: casts, LayerNorm fwd/bwd, bias-gradient column sums, patch gathering,
+// TimeSformer embedding assembly / temporal pooling, BERT embedding gather/scatter, fusion-input gather/concat.
+// All are written for coalesced 128-bit accesses with one warp per token row where a row reduction is needed.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace alpro {
+namespace {
+
+constexpr int LN_MAX_V4 = 8;  // per-lane float4 registers -> d <= 1024
+
+__device__ __forceinline__ float load_any(const void* p, int kind, long long idx) {
+  if (kind == 0) return reinterpret_cast<const float*>(p)[idx];
+  return f16_to_32(reinterpret_cast<const uint16_t*>(p)[idx], kind - 1);
+}
+
+// ------------------------------------------------------------------------------------------------ cast
+__global__ void cast_f32_to_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n, int fmt) {
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint2 w;
+    w.x = pack2_16(v.x, v.y, fmt);
+    w.y = pack2_16(v.z, v.w, fmt);
+    *reinterpret_cast<uint2*>(dst + i) = w;
+  }
+  if (i < n) {  // tail (n % 4 != 0): handled by the thread whose window crosses n
+    for (long long j = i; j < n; ++j) dst[j] = f32_to_16(src[j], fmt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm fwd
+// One warp per row; two-pass statistics held in registers (matches torch: var = mean((x-mean)^2), biased).
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, long long M, int d,
+                                     float* __restrict__ out32, long long ld32, uint16_t* __restrict__ out16,
+                                     long long ld16, int fmt, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nv = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[LN_MAX_V4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      v[i] = xr[c];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out32) reinterpret_cast<float4*>(out32 + row * ld32)[c] = y;
+      if (out16) {
+        uint2 w;
+        w.x = pack2_16(y.x, y.y, fmt);
+        w.y = pack2_16(y.z, y.w, fmt);
+        reinterpret_cast<uint2*>(out16 + row * ld16)[c] = w;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm bwd
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += dy*xhat; dbeta += dy.
+// Each warp walks rows with a grid stride and keeps its dgamma/dbeta partials in registers; one block-level
+// reduction + fp32 atomics at the end.
+__global__ void layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, long long lddy,
+                                     const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, const float* __restrict__ gamma, long long M,
+                                     int d, float* __restrict__ dx32, long long lddx, int accumulate,
+                                     uint16_t* __restrict__ dx16, long long lddx16, int fmt, int zero_period,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float red[];  // [warps][d] x 2
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int nv = d >> 2;
+  float4 ag[LN_MAX_V4], ab[LN_MAX_V4];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (long long row = static_cast<long long>(blockIdx.x) * nwarps + warp; row < M;
+       row += static_cast<long long>(gridDim.x) * nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[LN_MAX_V4], g[LN_MAX_V4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        const float4 xv = reinterpret_cast<const float4*>(x + row * ldx)[c];
+        float4 dv;
+        if (dy_kind == 0) {
+          dv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * lddy)[c];
+        } else {
+          const uint2 w = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy) + row * lddy)[c];
+          dv.x = f16_to_32(static_cast<uint16_t>(w.x & 0xffff), dy_kind - 1);
+          dv.y = f16_to_32(static_cast<uint16_t>(w.x >> 16), dy_kind - 1);
+          dv.z = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), dy_kind - 1);
+          dv.w = f16_to_32(static_cast<uint16_t>(w.y >> 16), dy_kind - 1);
+        }
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      }
+    }
+    const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
+    const bool zero16 = zero_period > 0 && (row % zero_period) == 0;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = rs * (g[i].x - c1 - xh[i].x * c2);
+        o.y = rs * (g[i].y - c1 - xh[i].y * c2);
+        o.z = rs * (g[i].z - c1 - xh[i].z * c2);
+        o.w = rs * (g[i].w - c1 - xh[i].w * c2);
+        float4* dst = reinterpret_cast<float4*>(dx32 + row * lddx) + c;
+        if (accumulate) {
+          const float4 p = *dst;
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *dst = o;
+        if (dx16) {
+          uint2 w;
+          if (zero16) {
+            w.x = w.y = 0u;
+          } else {
+            w.x = pack2_16(o.x, o.y, fmt);
+            w.y = pack2_16(o.z, o.w, fmt);
+          }
+          reinterpret_cast<uint2*>(dx16 + row * lddx16)[c] = w;
+        }
+      }
+    }
+  }
+  if (!dgamma && !dbeta) return;
+  float* rg = red;
+  float* rb = red + nwarps * d;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      reinterpret_cast<float4*>(rg + warp * d)[c] = ag[i];
+      reinterpret_cast<float4*>(rb + warp * d)[c] = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      sg += rg[w * d + c];
+      sb += rb[w * d + c];
+    }
+    if (dgamma) atomicAdd(dgamma + c, sg);
+    if (dbeta) atomicAdd(dbeta + c, sb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[n] += alpha * sum_m x[m,n]   (bias gradients). grid = (ceil(N/256), row_chunks); 128 threads x 2 columns.
+__global__ void colsum16_kernel(const uint16_t* __restrict__ x, int fmt, long long ld, long long M, int N,
+                                float* __restrict__ out, float alpha, int zero_period) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (col >= N) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (long long r = blockIdx.y; r < M; r += gridDim.y) {
+    if (zero_period > 0 && (r % zero_period) == 0) continue;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(x + r * ld + col);
+    s0 += f16_to_32(static_cast<uint16_t>(w & 0xffff), fmt);
+    s1 += f16_to_32(static_cast<uint16_t>(w >> 16), fmt);
+  }
+  atomicAdd(out + col, s0 * alpha);
+  if (col + 1 < N) atomicAdd(out + col + 1, s1 * alpha);
+}
+
+__global__ void colsum32_kernel(const float* __restrict__ x, long long ld, long long M, int N, float* __restrict__ out,
+                                float alpha) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float s = 0.f;
+  for (long long r = blockIdx.y; r < M; r += gridDim.y) s += x[r * ld + col];
+  atomicAdd(out + col, s * alpha);
+}
+
+// ------------------------------------------------------------------------------------------------ patch gather
+// frames fp32 [B,T,3,H,W] -> 16-bit patch matrix [B*(1+N*T), 3*P*P] in the canonical token order
+// (row b*(1+N*T) + 1 + n*T + t; row b*(1+N*T) is the clip's cls slot and is zero-filled). Column index
+// c*P*P + ky*P + kx matches Conv2d weight [d,3,P,P].view(d,-1) (PatchEmbed, vit.py:230-238).
+__global__ void patchify_kernel(const float* __restrict__ frames, uint16_t* __restrict__ out, int fmt, int B, int T,
+                                int H, int W, int P) {
+  const int gw = W / P, gh = H / P;
+  const int N = gw * gh;
+  const int Kd = 3 * P * P;
+  const int k4 = Kd >> 2;
+  const long long rows = static_cast<long long>(B) * (1 + N * T);
+  const long long total = rows * k4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / k4;
+    const int k = static_cast<int>(i - row * k4) * 4;
+    const int b = static_cast<int>(row / (1 + N * T));
+    const int j = static_cast<int>(row - static_cast<long long>(b) * (1 + N * T));
+    uint2 w = make_uint2(0u, 0u);
+    if (j > 0) {
+      const int n = (j - 1) / T, t = (j - 1) - n * T;
+      const int py = n / gw, px = n - py * gw;
+      const int c = k / (P * P);
+      const int rem = k - c * P * P;
+      const int ky = rem / P, kx = rem - ky * P;
+      const float4 v = *reinterpret_cast<const float4*>(
+          frames + (((static_cast<long long>(b) * T + t) * 3 + c) * H + (py * P + ky)) * W + px * P + kx);
+      w.x = pack2_16(v.x, v.y, fmt);
+      w.y = pack2_16(v.z, v.w, fmt);
+    }
+    *reinterpret_cast<uint2*>(out + row * Kd + k) = w;
+  }
+}
+
+// x[b,0] = cls + pos[0];  x[b,1+n*T+t] = proj[b,1+n*T+t] + pos[1+n] + time[t]      (vit.py:324-361)
+__global__ void vit_embed_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ cls,
+                                     const float* __restrict__ pos, const float* __restrict__ tim,
+                                     float* __restrict__ x, int B, int N, int T, int d) {
+  const int d4 = d >> 2;
+  const long long total = static_cast<long long>(B) * (1 + N * T) * d4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    const int j = static_cast<int>(row % (1 + N * T));
+    float4 o;
+    if (j == 0) {
+      const float4 a = reinterpret_cast<const float4*>(cls)[c];
+      const float4 p = reinterpret_cast<const float4*>(pos)[c];
+      o = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    } else {
+      const int n = (j - 1) / T, t = (j - 1) - n * T;
+      const float4 a = reinterpret_cast<const float4*>(proj)[i];
+      const float4 p = reinterpret_cast<const float4*>(pos + static_cast<long long>(1 + n) * d)[c];
+      const float4 q = reinterpret_cast<const float4*>(tim + static_cast<long long>(t) * d)[c];
+      o = make_float4(a.x + p.x + q.x, a.y + p.y + q.y, a.z + p.z + q.z, a.w + p.w + q.w);
+    }
+    reinterpret_cast<float4*>(x)[i] = o;
+  }
+}
+
+// Gradients of cls_token / pos_embed / time_embed: reductions of dx over (b,t), (b,n), b.
+// grid.x = 1 + N + T blocks, one output row each; threads over d; atomics not needed.
+__global__ void vit_embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
+                                     float* __restrict__ dtim, int B, int N, int T, int d, float alpha) {
+  const int which = blockIdx.x;
+  const long long S = 1 + static_cast<long long>(N) * T;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float s = 0.f;
+    if (which == 0) {
+      for (int b = 0; b < B; ++b) s += dx[(b * S) * d + c];
+      dcls[c] = s * alpha;
+      dpos[c] = s * alpha;
+    } else if (which <= N) {
+      const int n = which - 1;
+      for (int b = 0; b < B; ++b)
+        for (int t = 0; t < T; ++t) s += dx[(b * S + 1 + static_cast<long long>(n) * T + t) * d + c];
+      dpos[static_cast<long long>(1 + n) * d + c] = s * alpha;
+    } else {
+      const int t = which - 1 - N;
+      for (int b = 0; b < B; ++b)
+        for (int n = 0; n < N; ++n) s += dx[(b * S + 1 + static_cast<long long>(n) * T + t) * d + c];
+      dtim[static_cast<long long>(t) * d + c] = s * alpha;
+    }
+  }
+}
+
+// video_embeds[b,0] = xn[b,0]; video_embeds[b,1+n] = mean_t xn[b,1+n*T+t]     (TimeSformer.forward_features :484-492)
+__global__ void temporal_pool_fwd_kernel(const float* __restrict__ xn, float* __restrict__ out, int B, int N, int T,
+                                         int d) {
+  const int d4 = d >> 2;
+  const long long total = static_cast<long long>(B) * (1 + N) * d4;
+  const float inv = 1.f / T;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    const int b = static_cast<int>(row / (1 + N));
+    const int j = static_cast<int>(row - static_cast<long long>(b) * (1 + N));
+    const float4* src = reinterpret_cast<const float4*>(xn + (static_cast<long long>(b) * (1 + N * T)) * d) + c;
+    float4 o;
+    if (j == 0) {
+      o = src[0];
+    } else {
+      o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < T; ++t) {
+        const float4 v = src[(1 + static_cast<long long>(j - 1) * T + t) * d4];
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      }
+      o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+__global__ void temporal_pool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dxn, int B, int N, int T,
+                                         int d, float alpha) {
+  const int d4 = d >> 2;
+  const long long total = static_cast<long long>(B) * (1 + N * T) * d4;
+  const float inv = alpha / T;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    const int b = static_cast<int>(row / (1 + N * T));
+    const int j = static_cast<int>(row - static_cast<long long>(b) * (1 + N * T));
+    const int jo = j == 0 ? 0 : 1 + (j - 1) / T;
+    const float4 v = reinterpret_cast<const float4*>(dout + (static_cast<long long>(b) * (1 + N) + jo) * d)[c];
+    const float s = j == 0 ? alpha : inv;
+    reinterpret_cast<float4*>(dxn)[i] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BERT embeddings
+// e[b,l] = word[ids[b,l]] + type[0] + pos[l]            (BertEmbeddings.forward xbert.py:186-210, before LayerNorm)
+__global__ void bert_embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
+                                         const float* __restrict__ pos, const float* __restrict__ type,
+                                         float* __restrict__ out, long long BL, int L, int h) {
+  const int h4 = h >> 2;
+  const long long total = BL * h4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long tok = i / h4;
+    const int c = static_cast<int>(i - tok * h4);
+    const int l = static_cast<int>(tok % L);
+    const float4 a = reinterpret_cast<const float4*>(word + ids[tok] * h)[c];
+    const float4 p = reinterpret_cast<const float4*>(pos + static_cast<long long>(l) * h)[c];
+    const float4 t = reinterpret_cast<const float4*>(type)[c];
+    reinterpret_cast<float4*>(out)[i] = make_float4(a.x + p.x + t.x, a.y + p.y + t.y, a.z + p.z + t.z, a.w + p.w + t.w);
+  }
+}
+
+__global__ void bert_embed_scatter_kernel(const long long* __restrict__ ids, const float* __restrict__ de,
+                                          float* __restrict__ dword, float* __restrict__ dpos,
+                                          float* __restrict__ dtype, long long BL, int L, int h, float alpha) {
+  const long long total = BL * h;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long tok = i / h;
+    const int c = static_cast<int>(i - tok * h);
+    const int l = static_cast<int>(tok % L);
+    const float v = de[i] * alpha;
+    atomicAdd(dword + ids[tok] * h + c, v);
+    atomicAdd(dpos + static_cast<long long>(l) * h + c, v);
+    atomicAdd(dtype + c, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fusion input
+// out[s] = cat(text[ti[s]] (L rows), video[vi[s]] (Nv rows));  add_mask[s] = (1 - cat(tmask[ti[s]], 1)) * -10000
+// (compute_vtm / compute_mlm embedding_output + get_extended_attention_mask; alpro_models.py:273-275,318-331,
+//  xbert.py:878-938). Index lists let positives, hard negatives and the MLM pass share one batched fusion pass.
+__global__ void fusion_gather_fwd_kernel(const float* __restrict__ text, const float* __restrict__ video,
+                                         const long long* __restrict__ tmask, const int* __restrict__ ti,
+                                         const int* __restrict__ vi, float* __restrict__ out32,
+                                         uint16_t* __restrict__ out16, int fmt, float* __restrict__ add_mask, int S,
+                                         int L, int Nv, int h) {
+  const int h4 = h >> 2;
+  const int R = L + Nv;
+  const long long total = static_cast<long long>(S) * R * h4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / h4;
+    const int c = static_cast<int>(i - row * h4);
+    const int s = static_cast<int>(row / R);
+    const int j = static_cast<int>(row - static_cast<long long>(s) * R);
+    float4 v;
+    if (j < L) {
+      v = reinterpret_cast<const float4*>(text + (static_cast<long long>(ti[s]) * L + j) * h)[c];
+      if (c == 0 && add_mask) add_mask[row] = (1.0f - static_cast<float>(tmask[static_cast<long long>(ti[s]) * L + j])) * -10000.0f;
+    } else {
+      v = reinterpret_cast<const float4*>(video + (static_cast<long long>(vi[s]) * Nv + (j - L)) * h)[c];
+      if (c == 0 && add_mask) add_mask[row] = 0.f;
+    }
+    reinterpret_cast<float4*>(out32)[i] = v;
+    if (out16) {
+      uint2 w;
+      w.x = pack2_16(v.x, v.y, fmt);
+      w.y = pack2_16(v.z, v.w, fmt);
+      reinterpret_cast<uint2*>(out16)[i] = w;
+    }
+  }
+}
+
+__global__ void fusion_gather_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ ti,
+                                         const int* __restrict__ vi, float* __restrict__ dtext,
+                                         float* __restrict__ dvideo, int S, int L, int Nv, int h) {
+  const int R = L + Nv;
+  const long long total = static_cast<long long>(S) * R * h;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / h;
+    const int c = static_cast<int>(i - row * h);
+    const int s = static_cast<int>(row / R);
+    const int j = static_cast<int>(row - static_cast<long long>(s) * R);
+    const float v = dout[i];
+    if (j < L) atomicAdd(dtext + (static_cast<long long>(ti[s]) * L + j) * h + c, v);
+    else atomicAdd(dvideo + (static_cast<long long>(vi[s]) * Nv + (j - L)) * h + c, v);
+  }
+}
+
+// mean over t of the T per-frame cls rows -> the clip's canonical cls row (Block.forward vit.py:184-187, moved in front
+// of the linear `proj`, with which the mean commutes).
+__global__ void cls_mean_fwd_kernel(const uint16_t* __restrict__ cls_t, uint16_t* __restrict__ o, long long ldo,
+                                    int fmt, int B, int T, int S, int d) {
+  // cls_t: [B, T, d]; o row b*S gets the mean
+  const long long total = static_cast<long long>(B) * d;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / d);
+    const int c = static_cast<int>(i - static_cast<long long>(b) * d);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += f16_to_32(cls_t[(static_cast<long long>(b) * T + t) * d + c], fmt);
+    o[static_cast<long long>(b) * S * ldo + c] = f32_to_16(s / T, fmt);
+  }
+}
+
+inline int grid_for(long long work_items, int block) {
+  long long g = cdiv(work_items, block);
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+}  // namespace alpro
+
+using namespace alpro;
+
+extern "C" int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int fmt, void* stream) {
+  ALPRO_REQUIRE(src && dst && n >= 0, "alpro_cast_f32_to_16: bad args");
+  if (n == 0) return 0;
+  ALPRO_REQUIRE(aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "alpro_cast_f32_to_16: alignment");
+  cast_f32_to_16_kernel<<<grid_for(cdiv(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<uint16_t*>(dst), n, fmt);
+  ALPRO_CHECK_LAUNCH("alpro_cast_f32_to_16");
+  return 0;
+}
+
+extern "C" int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                                   int64_t M, int d, float* out32, int64_t ld32, void* out16, int64_t ld16,
+                                   int out16_fmt, float* mean, float* rstd, void* stream) {
+  ALPRO_REQUIRE(x && gamma && beta && M > 0, "alpro_layernorm_fwd: bad args");
+  ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_fwd: d=%d unsupported (multiple of 4, <= 1024)", d);
+  ALPRO_REQUIRE(ldx % 4 == 0 && (!out32 || ld32 % 4 == 0) && (!out16 || ld16 % 4 == 0), "alpro_layernorm_fwd: ld");
+  const int wpb = 8;
+  layernorm_fwd_kernel<<<static_cast<unsigned>(cdiv(M, wpb)), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, gamma, beta, eps, M, d, out32, ld32, static_cast<uint16_t*>(out16), ld16, out16_fmt, mean, rstd);
+  ALPRO_CHECK_LAUNCH("alpro_layernorm_fwd");
+  return 0;
+}
+
+extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, const float* x, int64_t ldx,
+                                   const float* mean, const float* rstd, const float* gamma, int64_t M, int d,
+                                   float* dx32, int64_t lddx, int accumulate, void* dx16, int64_t lddx16,
+                                   int dx16_fmt, int zero_period, float* dgamma, float* dbeta, void* stream) {
+  ALPRO_REQUIRE(dy && x && mean && rstd && gamma && dx32 && M > 0, "alpro_layernorm_bwd: bad args");
+  ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_bwd: d=%d unsupported", d);
+  ALPRO_REQUIRE(dy_kind >= 0 && dy_kind <= 2, "alpro_layernorm_bwd: dy_kind");
+  const int wpb = 8;
+  int grid = static_cast<int>(cdiv(M, wpb));
+  const int cap = num_sms() * 4;
+  if (grid > cap) grid = cap;
+  const size_t smem = static_cast<size_t>(2) * wpb * d * sizeof(float);
+  layernorm_bwd_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, accumulate, static_cast<uint16_t*>(dx16), lddx16,
+      dx16_fmt, zero_period, dgamma, dbeta);
+  ALPRO_CHECK_LAUNCH("alpro_layernorm_bwd");
+  return 0;
+}
+
+extern "C" int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int N, float* out, float alpha,
+                            int zero_period, void* stream) {
+  ALPRO_REQUIRE(x && out && M > 0 && N > 0, "alpro_colsum: bad args");
+  int rows = static_cast<int>(M < 512 ? M : 512);
+  if (kind == 0) {
+    dim3 grid(static_cast<unsigned>(cdiv(N, 128)), rows);
+    colsum32_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ld, M, N, out,
+                                                                          alpha);
+  } else {
+    ALPRO_REQUIRE(ld % 2 == 0, "alpro_colsum: ld must be even for 16-bit input");
+    dim3 grid(static_cast<unsigned>(cdiv(N, 256)), rows);
+    colsum16_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(x), kind - 1, ld,
+                                                                          M, N, out, alpha, zero_period);
+  }
+  ALPRO_CHECK_LAUNCH("alpro_colsum");
+  return 0;
+}
+
+extern "C" int alpro_patchify(const float* frames, void* out16, int fmt, int B, int T, int H, int W, int P,
+                              void* stream) {
+  ALPRO_REQUIRE(frames && out16 && B > 0 && T > 0, "alpro_patchify: bad args");
+  ALPRO_REQUIRE(P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "alpro_patchify: P=%d H=%d W=%d unsupported", P, H, W);
+  const long long total = static_cast<long long>(B) * (1 + (H / P) * (W / P) * T) * (3 * P * P / 4);
+  patchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, static_cast<uint16_t*>(out16), fmt, B, T, H, W, P);
+  ALPRO_CHECK_LAUNCH("alpro_patchify");
+  return 0;
+}
+
+extern "C" int alpro_vit_embed_fwd(const float* proj, const float* cls, const float* pos, const float* tim, float* x,
+                                   int B, int N, int T, int d, void* stream) {
+  ALPRO_REQUIRE(proj && cls && pos && tim && x && d % 4 == 0, "alpro_vit_embed_fwd: bad args");
+  const long long total = static_cast<long long>(B) * (1 + N * T) * (d / 4);
+  vit_embed_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(proj, cls, pos, tim, x, B,
+                                                                                           N, T, d);
+  ALPRO_CHECK_LAUNCH("alpro_vit_embed_fwd");
+  return 0;
+}
+
+extern "C" int alpro_vit_embed_bwd(const float* dx, float* dcls, float* dpos, float* dtim, int B, int N, int T, int d,
+                                   float alpha, void* stream) {
+  ALPRO_REQUIRE(dx && dcls && dpos && dtim, "alpro_vit_embed_bwd: bad args");
+  vit_embed_bwd_kernel<<<1 + N + T, 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, dcls, dpos, dtim, B, N, T, d,
+                                                                                 alpha);
+  ALPRO_CHECK_LAUNCH("alpro_vit_embed_bwd");
+  return 0;
+}
+
+extern "C" int alpro_temporal_pool_fwd(const float* xn, float* out, int B, int N, int T, int d, void* stream) {
+  ALPRO_REQUIRE(xn && out && d % 4 == 0, "alpro_temporal_pool_fwd: bad args");
+  const long long total = static_cast<long long>(B) * (1 + N) * (d / 4);
+  temporal_pool_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xn, out, B, N, T, d);
+  ALPRO_CHECK_LAUNCH("alpro_temporal_pool_fwd");
+  return 0;
+}
+
+extern "C" int alpro_temporal_pool_bwd(const float* dout, float* dxn, int B, int N, int T, int d, float alpha,
+                                       void* stream) {
+  ALPRO_REQUIRE(dout && dxn && d % 4 == 0, "alpro_temporal_pool_bwd: bad args");
+  const long long total = static_cast<long long>(B) * (1 + N * T) * (d / 4);
+  temporal_pool_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, dxn, B, N, T, d,
+                                                                                               alpha);
+  ALPRO_CHECK_LAUNCH("alpro_temporal_pool_bwd");
+  return 0;
+}
+
+extern "C" int alpro_bert_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type,
+                                       float* out, int64_t BL, int L, int h, void* stream) {
+  ALPRO_REQUIRE(ids && word && pos && type && out && h % 4 == 0, "alpro_bert_embed_gather: bad args");
+  bert_embed_gather_kernel<<<grid_for(BL * (h / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), word, pos, type, out, BL, L, h);
+  ALPRO_CHECK_LAUNCH("alpro_bert_embed_gather");
+  return 0;
+}
+
+extern "C" int alpro_bert_embed_scatter(const int64_t* ids, const float* de, float* dword, float* dpos, float* dtype,
+                                        int64_t BL, int L, int h, float alpha, void* stream) {
+  ALPRO_REQUIRE(ids && de && dword && dpos && dtype, "alpro_bert_embed_scatter: bad args");
+  bert_embed_scatter_kernel<<<grid_for(BL * h, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), de, dword, dpos, dtype, BL, L, h, alpha);
+  ALPRO_CHECK_LAUNCH("alpro_bert_embed_scatter");
+  return 0;
+}
+
+extern "C" int alpro_fusion_gather_fwd(const float* text, const float* video, const int64_t* tmask, const int32_t* ti,
+                                       const int32_t* vi, float* out32, void* out16, int fmt, float* add_mask, int S,
+                                       int L, int Nv, int h, void* stream) {
+  ALPRO_REQUIRE(text && video && tmask && ti && vi && out32 && h % 4 == 0, "alpro_fusion_gather_fwd: bad args");
+  const long long total = static_cast<long long>(S) * (L + Nv) * (h / 4);
+  fusion_gather_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      text, video, reinterpret_cast<const long long*>(tmask), ti, vi, out32, static_cast<uint16_t*>(out16), fmt,
+      add_mask, S, L, Nv, h);
+  ALPRO_CHECK_LAUNCH("alpro_fusion_gather_fwd");
+  return 0;
+}
+
+extern "C" int alpro_fusion_gather_bwd(const float* dout, const int32_t* ti, const int32_t* vi, float* dtext,
+                                       float* dvideo, int S, int L, int Nv, int h, void* stream) {
+  ALPRO_REQUIRE(dout && ti && vi && dtext && dvideo, "alpro_fusion_gather_bwd: bad args");
+  const long long total = static_cast<long long>(S) * (L + Nv) * h;
+  fusion_gather_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, ti, vi, dtext,
+                                                                                               dvideo, S, L, Nv, h);
+  ALPRO_CHECK_LAUNCH("alpro_fusion_gather_bwd");
+  return 0;
+}
+
+extern "C" int alpro_cls_mean_fwd(const void* cls_t, void* o, int64_t ldo, int fmt, int B, int T, int S, int d,
+                                  void* stream) {
+  ALPRO_REQUIRE(cls_t && o, "alpro_cls_mean_fwd: bad args");
+  cls_mean_fwd_kernel<<<grid_for(static_cast<long long>(B) * d, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(cls_t), static_cast<uint16_t*>(o), ldo, fmt, B, T, S, d);
+  ALPRO_CHECK_LAUNCH("alpro_cls_mean_fwd");
+  return 0;
+}
