@@ -1,12 +1,15 @@
-"""ctypes binding of libalpro_b200.so (the C-ABI declared in include/alpro_b200.h).
+"""ctypes binding of libalpro_b200.so. Signatures are read from include/alpro_b200.h (the single source of truth for
+the C-ABI), so every declared entry point must be exported by the library or the import fails loudly.
 
-The product path has no fallback: if the shared library is missing or a symbol cannot be resolved, import fails loudly.
+The product path has no fallback: if the shared library is missing or a symbol cannot be resolved, import fails.
 """
 import ctypes
 import os
+import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libalpro_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "alpro_b200.h")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
@@ -38,29 +41,46 @@ def _load():
     return ctypes.CDLL(LIB_PATH)
 
 
+def parse_header(path=HEADER_PATH):
+    """Returns {name: (restype, [argtypes])} for every function prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", " ", src)
+    protos = {}
+    for m in re.finditer(r"\b(int|const char\s*\*)\s+(alpro_\w+)\s*\(([^;{]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        restype = c_int if ret == "int" else ctypes.c_char_p
+        argtypes = []
+        args = args.strip()
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "AlproGemmEpilogue" in a:
+                    argtypes.append(ctypes.POINTER(GemmEpilogue))
+                elif "*" in a:
+                    argtypes.append(c_void_p)
+                elif re.match(r"(const )?int64_t\b", a):
+                    argtypes.append(c_int64)
+                elif re.match(r"(const )?(int|int32_t)\b", a):
+                    argtypes.append(c_int)
+                elif re.match(r"(const )?float\b", a):
+                    argtypes.append(c_float)
+                else:
+                    raise ImportError(f"alpro_b200.h: cannot map argument '{a}' of {name}")
+        protos[name] = (restype, argtypes)
+    return protos
+
+
 lib = _load()
-
-# name -> (restype, argtypes); every symbol declared in include/alpro_b200.h must be listed here
-# (tests/test_abi.py cross-checks this table against the header).
-_SIGS = {}
-
-
-def _sig(name, argtypes, restype=c_int):
-    fn = getattr(lib, name)  # AttributeError if the symbol is missing -> loud failure
-    fn.restype = restype
-    fn.argtypes = argtypes
-    _SIGS[name] = fn
-    return fn
-
-
-alpro_last_error = _sig("alpro_last_error", [], ctypes.c_char_p)
-alpro_version = _sig("alpro_version", [])
-alpro_num_sms = _sig("alpro_num_sms", [])
-alpro_gemm16 = _sig("alpro_gemm16", [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
-                                     c_int, c_int, c_int, c_int, ctypes.POINTER(GemmEpilogue), c_void_p])
+PROTOS = parse_header()
+for _name, (_res, _args) in PROTOS.items():
+    _fn = getattr(lib, _name)  # AttributeError if the symbol is missing -> loud failure
+    _fn.restype = _res
+    _fn.argtypes = _args
+    globals()[_name] = _fn
 
 
 def check(rc, what=""):
     if rc != 0:
-        msg = alpro_last_error()
+        msg = lib.alpro_last_error()
         raise AlproError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -98,7 +98,7 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, l
                                      const float* __restrict__ rstd, const float* __restrict__ gamma, long long M,
                                      int d, float* __restrict__ dx32, long long lddx, int accumulate,
                                      uint16_t* __restrict__ dx16, long long lddx16, int fmt, int zero_period,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float param_scale) {
   extern __shared__ float red[];  // [warps][d] x 2
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -185,8 +185,8 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, l
       sg += rg[w * d + c];
       sb += rb[w * d + c];
     }
-    if (dgamma) atomicAdd(dgamma + c, sg);
-    if (dbeta) atomicAdd(dbeta + c, sb);
+    if (dgamma) atomicAdd(dgamma + c, sg * param_scale);
+    if (dbeta) atomicAdd(dbeta + c, sb * param_scale);
   }
 }
 
@@ -492,7 +492,8 @@ extern "C" int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gam
 extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, const float* x, int64_t ldx,
                                    const float* mean, const float* rstd, const float* gamma, int64_t M, int d,
                                    float* dx32, int64_t lddx, int accumulate, void* dx16, int64_t lddx16,
-                                   int dx16_fmt, int zero_period, float* dgamma, float* dbeta, void* stream) {
+                                   int dx16_fmt, int zero_period, float* dgamma, float* dbeta, float param_scale,
+                                   void* stream) {
   ALPRO_REQUIRE(dy && x && mean && rstd && gamma && dx32 && M > 0, "alpro_layernorm_bwd: bad args");
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_bwd: d=%d unsupported", d);
   ALPRO_REQUIRE(dy_kind >= 0 && dy_kind <= 2, "alpro_layernorm_bwd: dy_kind");
@@ -503,7 +504,7 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
   const size_t smem = static_cast<size_t>(2) * wpb * d * sizeof(float);
   layernorm_bwd_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, accumulate, static_cast<uint16_t*>(dx16), lddx16,
-      dx16_fmt, zero_period, dgamma, dbeta);
+      dx16_fmt, zero_period, dgamma, dbeta, param_scale);
   ALPRO_CHECK_LAUNCH("alpro_layernorm_bwd");
   return 0;
 }

@@ -61,6 +61,17 @@ struct GemmKParams {
   float alpha;
 };
 
+// Compile-time epilogue modes (each is one kernel instantiation; E_GENERIC keeps every flag at run time).
+enum EpiMode {
+  E_OUT16 = 0,        // out16 = acc*alpha + bias
+  E_GELU_SAVE = 1,    // out16b = pre-activation, out16 = gelu(pre)
+  E_GELU_GRAD = 2,    // out16 = acc*alpha * gelu'(aux)
+  E_RESID_OUT32 = 3,  // out32 = acc*alpha + bias + resid (skip_period rows: resid only); optional out16 copy
+  E_OUT32 = 4,        // out32 = acc*alpha + bias
+  E_ATOMIC = 5,       // out32 += acc*alpha   (split-K)
+  E_GENERIC = 6
+};
+
 __device__ __forceinline__ void store4_16(uint16_t* o, const float (&v)[4], int fmt, bool full, int ncol) {
   if (full) {
     uint2 w;
@@ -73,80 +84,101 @@ __device__ __forceinline__ void store4_16(uint16_t* o, const float (&v)[4], int 
       if (j < ncol) o[j] = f32_to_16(v[j], fmt);
   }
 }
-
-// Epilogue for 4 consecutive columns of one row (coalesced side: 8 lanes cover 32 consecutive columns).
-// `b4` = bias for these 4 columns (already loaded), `r4` = residual (already loaded when vectorisable).
-__device__ __forceinline__ void epilogue4(const GemmKParams& p, float (&v)[4], const float4& b4, long long row, int col,
-                                          bool atomic) {
-  const int ncol = min(4, p.N - col);
-  const bool full = p.vec_ok && ncol == 4;
-  if (atomic) {
-    float* o = p.out32 + row * p.ld32 + col;
+__device__ __forceinline__ void load4_16(const uint16_t* a, float (&u)[4], int fmt, bool full, int ncol) {
+  if (full) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(a));
+    u[0] = f16_to_32(static_cast<uint16_t>(w.x & 0xffff), fmt);
+    u[1] = f16_to_32(static_cast<uint16_t>(w.x >> 16), fmt);
+    u[2] = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), fmt);
+    u[3] = f16_to_32(static_cast<uint16_t>(w.y >> 16), fmt);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = (j < ncol) ? f16_to_32(a[j], fmt) : 0.f;
+  }
+}
+__device__ __forceinline__ void load4_32(const float* r, float (&u)[4], bool full, int ncol) {
+  if (full) {
+    const float4 t = *reinterpret_cast<const float4*>(r);
+    u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = (j < ncol) ? r[j] : 0.f;
+  }
+}
+__device__ __forceinline__ void store4_32(float* o, const float (&v)[4], bool full, int ncol) {
+  if (full) {
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (j < ncol) atomicAdd(o + j, v[j]);  // result unused -> RED.ADD.F32
-    return;
+      if (j < ncol) o[j] = v[j];
   }
-  v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
-  if (p.act != ALPRO_ACT_NONE) {
-    if (p.act == ALPRO_ACT_GELU || p.act == ALPRO_ACT_RELU) {
-      if (p.out16b) store4_16(p.out16b + row * p.ld16b + col, v, p.out16b_fmt, full, ncol);
-      if (p.act == ALPRO_ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-    } else {  // *_GRAD: multiply by f'(aux)
-      float u[4];
-      const uint16_t* a = p.aux16 + row * p.ldaux + col;
-      if (full) {
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(a));
-        u[0] = f16_to_32(static_cast<uint16_t>(w.x & 0xffff), p.aux_fmt);
-        u[1] = f16_to_32(static_cast<uint16_t>(w.x >> 16), p.aux_fmt);
-        u[2] = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), p.aux_fmt);
-        u[3] = f16_to_32(static_cast<uint16_t>(w.y >> 16), p.aux_fmt);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) u[j] = (j < ncol) ? f16_to_32(a[j], p.aux_fmt) : 0.f;
-      }
-      if (p.act == ALPRO_ACT_GELU_GRAD) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(u[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = u[j] > 0.f ? v[j] : 0.f;
-      }
-    }
-  }
-  if (p.resid) {
-    const bool skip = p.skip_period > 0 && (row % p.skip_period) == 0;
-    const float* r = p.resid + row * p.ldresid + col;
-    float rr[4];
-    if (full) {
-      const float4 r4 = *reinterpret_cast<const float4*>(r);
-      rr[0] = r4.x; rr[1] = r4.y; rr[2] = r4.z; rr[3] = r4.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rr[j] = (j < ncol) ? r[j] : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = skip ? rr[j] : v[j] + rr[j];
-  }
-  if (p.out32) {
-    float* o = p.out32 + row * p.ld32 + col;
-    if (full) {
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < ncol) o[j] = v[j];
-    }
-  }
-  if (p.out16) store4_16(p.out16 + row * p.ld16 + col, v, p.out16_fmt, full, ncol);
 }
 
+// Epilogue for up to NR rows x 4 consecutive columns held by one lane on the coalesced side. All global loads of the
+// group are issued before any store so that they overlap (the compiler cannot hoist them itself: resid may alias out).
+template <int MODE, int NR>
+__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[NR][4], const float4& b4,
+                                              const long long (&row)[NR], const bool (&ok)[NR], int col) {
+  const int ncol = min(4, p.N - col);
+  const bool full = p.vec_ok && ncol == 4;
+  if (MODE == E_ATOMIC) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if (ok[i]) {
+        float* o = p.out32 + row[i] * p.ld32 + col;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < ncol) atomicAdd(o + j, v[i][j]);  // result unused -> RED.ADD.F32
+      }
+    return;
+  }
+  const int act = (MODE == E_GENERIC) ? p.act
+                  : (MODE == E_GELU_SAVE) ? ALPRO_ACT_GELU
+                  : (MODE == E_GELU_GRAD) ? ALPRO_ACT_GELU_GRAD : ALPRO_ACT_NONE;
+  const bool has_resid = (MODE == E_GENERIC) ? (p.resid != nullptr) : (MODE == E_RESID_OUT32);
+  const bool has_out32 = (MODE == E_GENERIC) ? (p.out32 != nullptr) : (MODE == E_RESID_OUT32 || MODE == E_OUT32);
+  const bool has_out16 = (MODE == E_GENERIC || MODE == E_RESID_OUT32) ? (p.out16 != nullptr)
+                                                                       : (MODE != E_OUT32);
+  const bool has_out16b = (MODE == E_GENERIC) ? (p.out16b != nullptr) : (MODE == E_GELU_SAVE);
+  float u[NR][4];
+  if (act == ALPRO_ACT_GELU_GRAD || act == ALPRO_ACT_RELU_GRAD) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if (ok[i]) load4_16(p.aux16 + row[i] * p.ldaux + col, u[i], p.aux_fmt, full, ncol);
+  } else if (has_resid) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if (ok[i]) load4_32(p.resid + row[i] * p.ldresid + col, u[i], full, ncol);
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (!ok[i]) continue;
+    v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w;
+    if (act == ALPRO_ACT_GELU || act == ALPRO_ACT_RELU) {
+      if (has_out16b) store4_16(p.out16b + row[i] * p.ld16b + col, v[i], p.out16b_fmt, full, ncol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = act == ALPRO_ACT_GELU ? gelu_erf(v[i][j]) : fmaxf(v[i][j], 0.f);
+    } else if (act == ALPRO_ACT_GELU_GRAD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] *= gelu_erf_grad(u[i][j]);
+    } else if (act == ALPRO_ACT_RELU_GRAD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = u[i][j] > 0.f ? v[i][j] : 0.f;
+    }
+    if (has_resid) {
+      if (MODE == E_GENERIC && (act == ALPRO_ACT_GELU_GRAD || act == ALPRO_ACT_RELU_GRAD))
+        load4_32(p.resid + row[i] * p.ldresid + col, u[i], full, ncol);  // rare combination: aux and resid
+      const bool skip = p.skip_period > 0 && (row[i] % p.skip_period) == 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = skip ? u[i][j] : v[i][j] + u[i][j];
+    }
+    if (has_out32) store4_32(p.out32 + row[i] * p.ld32 + col, v[i], full, ncol);
+    if (has_out16) store4_16(p.out16 + row[i] * p.ld16 + col, v[i], p.out16_fmt, full, ncol);
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -275,9 +307,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     float* stg = reinterpret_cast<float*>(sEpi + (warp - 4) * EPI_WARP_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool atomic = p.split_k > 1;
     const int crow = lane >> 3;  // 0..3
     const int cch = lane & 7;    // float4 index within the 32-column chunk
+    const float alpha = p.alpha;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int tile = w / p.split_k;
       const int m_blk = tile / p.num_n_tiles;
@@ -286,24 +318,28 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_after();
       const long long row0 = static_cast<long long>(m_blk) * BM + q * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const int c_begin = half * (BN / 2), c_end = (half + 1) * (BN / 2);
+      uint32_t r[32];
+      bool have = n_blk * BN + c_begin < p.N;  // warp-uniform
+      if (have) tmem_ld_32x32(taddr + c_begin, r);
 #pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += EPI_CHUNK) {
+      for (int c = c_begin; c < c_end && have; c += EPI_CHUNK) {
         const int col0 = n_blk * BN + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 t = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
-                                 __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+          float4 t = make_float4(__uint_as_float(r[4 * j]) * alpha, __uint_as_float(r[4 * j + 1]) * alpha,
+                                 __uint_as_float(r[4 * j + 2]) * alpha, __uint_as_float(r[4 * j + 3]) * alpha);
           *reinterpret_cast<float4*>(stg + lane * EPI_CHUNK + ((j ^ (lane & 7)) << 2)) = t;
         }
         __syncwarp();
+        // prefetch the next chunk's accumulators while this one is written out
+        have = (c + EPI_CHUNK < c_end) && (col0 + EPI_CHUNK < p.N);
+        if (have) tmem_ld_32x32(taddr + c + EPI_CHUNK, r);
         const int col = col0 + cch * 4;
         if (col < p.N) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && !atomic) {
+          if (MODE != E_ATOMIC && MODE != E_GELU_GRAD && p.bias) {
             if (p.vec_ok && col + 4 <= p.N) {
               b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             } else {
@@ -314,14 +350,19 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = crow + 4 * i;
-            const long long row = row0 + rl;
-            if (row < p.M) {
+          for (int i0 = 0; i0 < 8; i0 += 4) {
+            float v[4][4];
+            long long rows[4];
+            bool ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = crow + 4 * (i0 + i);
+              rows[i] = row0 + rl;
+              ok[i] = rows[i] < p.M;
               const float4 t = *reinterpret_cast<const float4*>(stg + rl * EPI_CHUNK + ((cch ^ (rl & 7)) << 2));
-              float v[4] = {t.x, t.y, t.z, t.w};
-              epilogue4(p, v, b4, row, col, atomic);
+              v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
             }
+            epilogue_rows<MODE, 4>(p, v, b4, rows, ok, col);
           }
         }
         __syncwarp();
@@ -457,13 +498,35 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   else         rc = make_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
 
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  });
+  int mode = E_GENERIC;
+  if (p.split_k > 1) mode = E_ATOMIC;
+  else if (p.act == ALPRO_ACT_NONE && !p.resid && !p.out32 && p.out16 && !p.out16b) mode = E_OUT16;
+  else if (p.act == ALPRO_ACT_GELU && !p.resid && !p.out32 && p.out16 && p.out16b) mode = E_GELU_SAVE;
+  else if (p.act == ALPRO_ACT_GELU_GRAD && !p.resid && !p.out32 && p.out16 && !p.out16b) mode = E_GELU_GRAD;
+  else if (p.act == ALPRO_ACT_NONE && p.resid && p.out32 && !p.out16b) mode = E_RESID_OUT32;
+  else if (p.act == ALPRO_ACT_NONE && !p.resid && p.out32 && !p.out16 && !p.out16b) mode = E_OUT32;
   const int work = tiles * p.split_k;
   const int grid = work < num_sms() ? work : num_sms();
-  gemm16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define ALPRO_LAUNCH_GEMM(M_)                                                                            \
+  case M_: {                                                                                             \
+    static std::once_flag once;                                                                          \
+    std::call_once(once, [] {                                                                            \
+      cudaFuncSetAttribute(gemm16_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
+    });                                                                                                  \
+    gemm16_kernel<M_><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);                               \
+  } break;
+  switch (mode) {
+    ALPRO_LAUNCH_GEMM(E_OUT16)
+    ALPRO_LAUNCH_GEMM(E_GELU_SAVE)
+    ALPRO_LAUNCH_GEMM(E_GELU_GRAD)
+    ALPRO_LAUNCH_GEMM(E_RESID_OUT32)
+    ALPRO_LAUNCH_GEMM(E_OUT32)
+    ALPRO_LAUNCH_GEMM(E_ATOMIC)
+    default:
+    ALPRO_LAUNCH_GEMM(E_GENERIC)
+  }
+#undef ALPRO_LAUNCH_GEMM
   ALPRO_CHECK_LAUNCH("alpro_gemm16");
   return 0;
 }

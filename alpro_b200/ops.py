@@ -93,3 +93,204 @@ def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, a
     ep.alpha = alpha
     check(_lib.alpro_gemm16(_ptr(a), _ptr(b), M, N, K, lda, ldb, a_layout, b_layout, _fmt(a), _fmt(b),
                             ctypes.byref(ep), _stream()), "alpro_gemm16")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# thin wrappers for the remaining entry points (argument order = include/alpro_b200.h)
+# ---------------------------------------------------------------------------------------------------------------------
+_KIND = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_L = _lib.lib
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def cast16(src, dst):
+    assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    check(_L.alpro_cast_f32_to_16(_p(src), _p(dst), src.numel(), _fmt(dst), _s()), "alpro_cast_f32_to_16")
+
+
+def layernorm_fwd(x, gamma, beta, eps, out32=None, out16=None, mean=None, rstd=None):
+    M, d = x.shape
+    check(_L.alpro_layernorm_fwd(_p(x), x.stride(0), _p(gamma), _p(beta), eps, M, d, _p(out32),
+                                 out32.stride(0) if out32 is not None else 0, _p(out16),
+                                 out16.stride(0) if out16 is not None else 0,
+                                 _fmt(out16) if out16 is not None else 0, _p(mean), _p(rstd), _s()), "alpro_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx32, accumulate, dx16=None, zero_period=0, dgamma=None, dbeta=None,
+                  param_scale=1.0):
+    M, d = x.shape
+    check(_L.alpro_layernorm_bwd(_p(dy), _KIND[dy.dtype], dy.stride(0), _p(x), x.stride(0), _p(mean), _p(rstd),
+                                 _p(gamma), M, d, _p(dx32), dx32.stride(0), int(accumulate), _p(dx16),
+                                 dx16.stride(0) if dx16 is not None else 0, _fmt(dx16) if dx16 is not None else 0,
+                                 zero_period, _p(dgamma), _p(dbeta), param_scale, _s()), "alpro_layernorm_bwd")
+
+
+def colsum(x, out, alpha=1.0, zero_period=0):
+    M, N = x.shape
+    check(_L.alpro_colsum(_p(x), _KIND[x.dtype], x.stride(0), M, N, _p(out), alpha, zero_period, _s()), "alpro_colsum")
+
+
+def patchify(frames, out16, P):
+    B, T, C, H, W = frames.shape
+    assert C == 3 and frames.is_contiguous() and frames.dtype == torch.float32
+    check(_L.alpro_patchify(_p(frames), _p(out16), _fmt(out16), B, T, H, W, P, _s()), "alpro_patchify")
+
+
+def vit_embed_fwd(proj, cls, pos, tim, x, B, N, T, d):
+    check(_L.alpro_vit_embed_fwd(_p(proj), _p(cls), _p(pos), _p(tim), _p(x), B, N, T, d, _s()), "alpro_vit_embed_fwd")
+
+
+def vit_embed_bwd(dx, dcls, dpos, dtim, B, N, T, d, alpha):
+    check(_L.alpro_vit_embed_bwd(_p(dx), _p(dcls), _p(dpos), _p(dtim), B, N, T, d, alpha, _s()), "alpro_vit_embed_bwd")
+
+
+def temporal_pool_fwd(xn, out, B, N, T, d):
+    check(_L.alpro_temporal_pool_fwd(_p(xn), _p(out), B, N, T, d, _s()), "alpro_temporal_pool_fwd")
+
+
+def temporal_pool_bwd(dout, dxn, B, N, T, d, alpha=1.0):
+    check(_L.alpro_temporal_pool_bwd(_p(dout), _p(dxn), B, N, T, d, alpha, _s()), "alpro_temporal_pool_bwd")
+
+
+def bert_embed_gather(ids, word, pos, type_, out, L, h):
+    check(_L.alpro_bert_embed_gather(_p(ids), _p(word), _p(pos), _p(type_), _p(out), ids.numel(), L, h, _s()),
+          "alpro_bert_embed_gather")
+
+
+def bert_embed_scatter(ids, de, dword, dpos, dtype_, L, h, alpha):
+    check(_L.alpro_bert_embed_scatter(_p(ids), _p(de), _p(dword), _p(dpos), _p(dtype_), ids.numel(), L, h, alpha, _s()),
+          "alpro_bert_embed_scatter")
+
+
+def fusion_gather_fwd(text, video, tmask, ti, vi, out32, out16, add_mask, S, L, Nv, h):
+    check(_L.alpro_fusion_gather_fwd(_p(text), _p(video), _p(tmask), _p(ti), _p(vi), _p(out32), _p(out16),
+                                     _fmt(out16) if out16 is not None else 0, _p(add_mask), S, L, Nv, h, _s()),
+          "alpro_fusion_gather_fwd")
+
+
+def fusion_gather_bwd(dout, ti, vi, dtext, dvideo, S, L, Nv, h):
+    check(_L.alpro_fusion_gather_bwd(_p(dout), _p(ti), _p(vi), _p(dtext), _p(dvideo), S, L, Nv, h, _s()),
+          "alpro_fusion_gather_bwd")
+
+
+def cls_mean_fwd(cls_t, o, B, T, clip_rows, d):
+    check(_L.alpro_cls_mean_fwd(_p(cls_t), _p(o), o.stride(0), _fmt(o), B, T, clip_rows, d, _s()), "alpro_cls_mean_fwd")
+
+
+def temporal_attn_fwd(qkv, out, B, N, T, heads, scale):
+    check(_L.alpro_temporal_attn_fwd(_p(qkv), qkv.stride(0), _p(out), out.stride(0), B, N, T, heads, _fmt(qkv), scale,
+                                     _s()), "alpro_temporal_attn_fwd")
+
+
+def temporal_attn_bwd(qkv, dout, dqkv, B, N, T, heads, scale):
+    check(_L.alpro_temporal_attn_bwd(_p(qkv), qkv.stride(0), _p(dout), dout.stride(0), _p(dqkv), dqkv.stride(0), B, N,
+                                     T, heads, _fmt(qkv), scale, _s()), "alpro_temporal_attn_bwd")
+
+
+def seq_attn_fwd(qkv, mask, o, cls_o, lse, S, nseq, heads, seq_div, stride, clip_rows, scale):
+    check(_L.alpro_seq_attn_fwd(_p(qkv), qkv.stride(0), _p(mask), _p(o), o.stride(0), _p(cls_o), _p(lse), S, nseq,
+                                heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()), "alpro_seq_attn_fwd")
+
+
+def seq_attn_bwd(qkv, mask, lse, dout, dqkv, scratch, S, nseq, heads, seq_div, stride, clip_rows, scale):
+    check(_L.alpro_seq_attn_bwd(_p(qkv), qkv.stride(0), _p(mask), _p(lse), _p(dout), dout.stride(0), _p(dqkv),
+                                _p(scratch), S, nseq, heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()),
+          "alpro_seq_attn_bwd")
+
+
+def small_linear_fwd(x, ldx, W, b, y, M, N, K, alpha=1.0, alpha_dev=None, alpha_mode=0, relu=False, ldw=None, ldy=None):
+    check(_L.alpro_small_linear_fwd(_p(x), ldx, _p(W), ldw if ldw is not None else K, _p(b), _p(y),
+                                    ldy if ldy is not None else N, M, N, K, alpha, _p(alpha_dev), alpha_mode,
+                                    int(relu), _s()), "alpro_small_linear_fwd")
+
+
+def small_linear_bwd(dy, lddy, yact, x, ldx, W, dx, lddx, dx_acc, dW, db, dw_acc, M, N, K, alpha=1.0, alpha_dev=None,
+                     alpha_mode=0, dw_scale=1.0, ldw=None, lddw=None):
+    check(_L.alpro_small_linear_bwd(_p(dy), lddy, _p(yact), lddy, _p(x), ldx, _p(W), ldw if ldw is not None else K,
+                                    _p(dx), lddx, int(dx_acc), _p(dW), lddw if lddw is not None else K, _p(db),
+                                    int(dw_acc), M, N, K, alpha, _p(alpha_dev), alpha_mode, dw_scale, _s()),
+          "alpro_small_linear_bwd")
+
+
+def l2norm_fwd(x, y, norm, eps=1e-12):
+    M, d = x.shape
+    check(_L.alpro_l2norm_fwd(_p(x), _p(y), _p(norm), M, d, eps, _s()), "alpro_l2norm_fwd")
+
+
+def l2norm_bwd(dy, y, norm, dx):
+    M, d = y.shape
+    check(_L.alpro_l2norm_bwd(_p(dy), _p(y), _p(norm), _p(dx), M, d, _s()), "alpro_l2norm_bwd")
+
+
+class CEState:
+    """Per-row statistics of one softmax-CE evaluation (kept for the backward)."""
+
+    def __init__(self, R, device):
+        self.buf = torch.empty(4, R, device=device, dtype=torch.float32)
+        self.scal = torch.empty(2, device=device, dtype=torch.float32)  # loss, denom
+
+    row_loss = property(lambda s: s.buf[0])
+    row_lse = property(lambda s: s.buf[1])
+    row_valid = property(lambda s: s.buf[2])
+    row_tsum = property(lambda s: s.buf[3])
+    loss = property(lambda s: s.scal[0])
+    denom = property(lambda s: s.scal[1:2])
+
+
+def softmax_ce_fwd(logits, C, hard=None, soft=None, row_ignore=None, denom_mode=0):
+    R = logits.shape[0]
+    st = CEState(R, logits.device)
+    check(_L.alpro_softmax_ce_fwd(_p(logits), logits.stride(0), R, C, _p(hard), _p(soft),
+                                  soft.stride(0) if soft is not None else 0, _p(row_ignore), _p(st.buf[0]),
+                                  _p(st.buf[1]), _p(st.buf[2]), _p(st.buf[3]), denom_mode, _p(st.scal[0:1]),
+                                  _p(st.scal[1:2]), _s()), "alpro_softmax_ce_fwd")
+    return st
+
+
+def softmax_ce_bwd(logits, C, st, gptr, gscale, hard=None, soft=None, out32=None, out16=None, C_out=None):
+    R = logits.shape[0]
+    out = out32 if out32 is not None else out16
+    check(_L.alpro_softmax_ce_bwd(_p(logits), logits.stride(0), R, C, _p(hard), _p(soft),
+                                  soft.stride(0) if soft is not None else 0, _p(st.buf[1]), _p(st.buf[2]),
+                                  _p(st.buf[3]), _p(st.scal[1:2]), _p(gptr), gscale, _p(out32), _p(out16),
+                                  _fmt(out16) if out16 is not None else 0, out.stride(0),
+                                  C_out if C_out is not None else C, _s()), "alpro_softmax_ce_bwd")
+
+
+def temp_grad(dsa, sa, dsb, sb, temp, dtemp, coef):
+    check(_L.alpro_temp_grad(_p(dsa), _p(sa), dsa.numel(), _p(dsb), _p(sb), dsb.numel() if dsb is not None else 0,
+                             _p(temp), _p(dtemp), coef, _s()), "alpro_temp_grad")
+
+
+def clamp_scalar(p, lo, hi):
+    check(_L.alpro_clamp_scalar(_p(p), lo, hi, _s()), "alpro_clamp_scalar")
+
+
+def masked_mean_fwd(x, seq_stride, row0, patch_mask, B, Np, h, out):
+    check(_L.alpro_masked_mean_fwd(_p(x), seq_stride, row0, _p(patch_mask), B, Np, h, _p(out), _s()),
+          "alpro_masked_mean_fwd")
+
+
+def masked_mean_bwd(dout, patch_mask, B, Np, h, dx, seq_stride, row0):
+    check(_L.alpro_masked_mean_bwd(_p(dout), _p(patch_mask), B, Np, h, _p(dx), seq_stride, row0, _s()),
+          "alpro_masked_mean_bwd")
+
+
+def take_rows_fwd(src, R, s0, n, L, h, out32=None, out16=None):
+    check(_L.alpro_take_rows_fwd(_p(src), R, s0, n, L, h, _p(out32), _p(out16),
+                                 _fmt(out16) if out16 is not None else 0, _s()), "alpro_take_rows_fwd")
+
+
+def take_rows_bwd(dout, R, s0, n, L, h, dsrc):
+    check(_L.alpro_take_rows_bwd(_p(dout), R, s0, n, L, h, _p(dsrc), _s()), "alpro_take_rows_bwd")
+
+
+def neg_weights(sim, col0, b, w):
+    check(_L.alpro_neg_weights(_p(sim), sim.stride(0), col0, b, _p(w), _s()), "alpro_neg_weights")

@@ -78,6 +78,109 @@ typedef struct AlproGemmEpilogue {
 int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                  int a_layout, int b_layout, int a_fmt, int b_fmt, const AlproGemmEpilogue* ep, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * HBM-bound row kernels (alpro_b200/csrc/elementwise.cu)
+ */
+/* fp32 -> 16-bit cast of a contiguous buffer (weight operand copies; replaces nothing in the reference, which runs fp32) */
+int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int fmt, void* stream);
+
+/* LayerNorm over the last dim (nn.LayerNorm: vit.py:113,119,127,279 eps 1e-6; xbert.py:177,354,433,658 eps 1e-12).
+ * x fp32 [M,d] -> out32 (optional) and/or out16 (optional); per-row mean / rstd saved for the backward. d%4==0, d<=1024 */
+int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int64_t M, int d,
+                        float* out32, int64_t ld32, void* out16, int64_t ld16, int out16_fmt, float* mean, float* rstd,
+                        void* stream);
+/* dy_kind 0 fp32 / 1 fp16 / 2 bf16. dx32 = (accumulate ? dx32 : 0) + LN'(dy); dx16 = 16-bit copy of the resulting dx32
+ * (rows with row % zero_period == 0 written as zero when zero_period > 0). dgamma/dbeta += param_scale * sums (atomics). */
+int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                        const float* rstd, const float* gamma, int64_t M, int d, float* dx32, int64_t lddx,
+                        int accumulate, void* dx16, int64_t lddx16, int dx16_fmt, int zero_period, float* dgamma,
+                        float* dbeta, float param_scale, void* stream);
+/* out[n] += alpha * sum_m x[m,n]; kind 0 fp32 / 1 fp16 / 2 bf16 (bias gradients of every nn.Linear on the path) */
+int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int N, float* out, float alpha, int zero_period,
+                 void* stream);
+/* PatchEmbed im2col (vit.py:233-239): frames fp32 [B,T,3,H,W] -> 16-bit [B*(1+N*T), 3*P*P], canonical token order
+ * row = b*(1+N*T) + 1 + n*T + t, with a zero row in every clip's cls slot */
+int alpro_patchify(const float* frames, void* out16, int fmt, int B, int T, int H, int W, int P, void* stream);
+/* x = cat(cls + pos[0], proj + pos[1+n] + time[t]) in 'b (n t)' order (vit.py:324-361) and its parameter gradients */
+int alpro_vit_embed_fwd(const float* proj, const float* cls, const float* pos, const float* tim, float* x, int B, int N,
+                        int T, int d, void* stream);
+int alpro_vit_embed_bwd(const float* dx, float* dcls, float* dpos, float* dtim, int B, int N, int T, int d, float alpha,
+                        void* stream);
+/* temporal mean pooling (TimeSformer.forward_features vit.py:484-492): [B,1+N*T,d] -> [B,1+N,d] */
+int alpro_temporal_pool_fwd(const float* xn, float* out, int B, int N, int T, int d, void* stream);
+int alpro_temporal_pool_bwd(const float* dout, float* dxn, int B, int N, int T, int d, float alpha, void* stream);
+/* BertEmbeddings (xbert.py:186-210) before its LayerNorm: word[ids] + type[0] + pos[l]; and the scatter-add backward */
+int alpro_bert_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type, float* out,
+                            int64_t BL, int L, int h, void* stream);
+int alpro_bert_embed_scatter(const int64_t* ids, const float* de, float* dword, float* dpos, float* dtype, int64_t BL,
+                             int L, int h, float alpha, void* stream);
+/* fusion-encoder input: out[s] = cat(text[ti[s]], video[vi[s]]), additive key mask (1-mask)*-1e4
+ * (alpro_models.py:273-275,318-331,354-357; xbert.py:878-938). ti/vi are int32 index lists on the device. */
+int alpro_fusion_gather_fwd(const float* text, const float* video, const int64_t* tmask, const int32_t* ti,
+                            const int32_t* vi, float* out32, void* out16, int fmt, float* add_mask, int S, int L, int Nv,
+                            int h, void* stream);
+int alpro_fusion_gather_bwd(const float* dout, const int32_t* ti, const int32_t* vi, float* dtext, float* dvideo, int S,
+                            int L, int Nv, int h, void* stream);
+/* mean over the T per-frame cls outputs [B,T,d] -> canonical cls row b*S of o (Block.forward vit.py:184-187) */
+int alpro_cls_mean_fwd(const void* cls_t, void* o, int64_t ldo, int fmt, int B, int T, int S, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Attention (alpro_b200/csrc/attention.cu), head_dim = 64
+ */
+/* temporal attention over the T frames of each patch position (vit.py:81-100 via :146-157); T in {1,2,4,8}.
+ * qkv [B*(1+N*T), 3d] canonical rows; cls rows are skipped (zero-filled in the outputs). */
+int alpro_temporal_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int B, int N, int T, int heads,
+                            int fmt, float scale, void* stream);
+int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const void* dout, int64_t ld_dout, void* dqkv,
+                            int64_t ld_dqkv, int B, int N, int T, int heads, int fmt, float scale, void* stream);
+/* sequence attention, S <= 256 keys, optional additive key mask [nseq,S] (vit.py:81-100 via :165-181;
+ * xbert.py:263-346). Token j of sequence s lives at row (s/seq_div)*clip_rows + (j==0 ? 0 : 1 + s%seq_div + (j-1)*stride):
+ *   BERT: seq_div=1, stride=1, clip_rows=S.   TimeSformer spatial: seq_div=T, stride=T, clip_rows=1+N*T, S=1+N.
+ * With seq_div>1 the per-frame cls outputs go to cls_o [nseq,d] (mean taken by alpro_cls_mean_fwd). lse: [nseq,heads,S]. */
+int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* mask, void* o, int64_t ld_o, void* cls_o, float* lse,
+                       int S, int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
+                       void* stream);
+int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* dout,
+                       int64_t ld_o, void* dqkv, float* dcls_qkv_scratch, int S, int nseq, int heads, int fmt, int seq_div,
+                       int stride, int64_t clip_rows, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Task-head kernels, fp32 (alpro_b200/csrc/heads.cu)
+ */
+/* y = act(alpha' * x W^T + b); alpha' = alpha (mode 0), alpha * *alpha_dev (1), alpha / *alpha_dev (2). Replaces the
+ * nn.Linear heads vision_proj/text_proj/itm_head/mpm_head and the sim = feat @ feats.t() / temp products
+ * (alpro_models.py:103,115-116,205,337,226). */
+int alpro_small_linear_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* b, float* y, int64_t ldy,
+                           int M, int N, int K, float alpha, const float* alpha_dev, int alpha_mode, int relu,
+                           void* stream);
+int alpro_small_linear_bwd(const float* dy, int64_t lddy, const float* yact, int64_t ldya, const float* x, int64_t ldx,
+                           const float* W, int64_t ldw, float* dx, int64_t lddx, int dx_accumulate, float* dW,
+                           int64_t lddw, float* db, int dw_accumulate, int M, int N, int K, float alpha,
+                           const float* alpha_dev, int alpha_mode, float dw_scale, void* stream);
+int alpro_l2norm_fwd(const float* x, float* y, float* norm, int M, int d, float eps, void* stream);
+int alpro_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx, int M, int d, void* stream);
+/* row-wise softmax cross-entropy with hard (int64, <0 ignored) or soft labels, loss = sum rows / denom
+ * (denom_mode 0: #valid rows, 1: R). F.cross_entropy / -sum(log_softmax*targets) at alpro_models.py:125-128,228-232,339,371. */
+int alpro_softmax_ce_fwd(const float* logits, int64_t ld, int R, int C, const int64_t* hard, const float* soft,
+                         int64_t ld_soft, const uint8_t* row_ignore, float* row_loss, float* row_lse, float* row_valid,
+                         float* row_tsum, int denom_mode, float* loss_out, float* denom_out, void* stream);
+int alpro_softmax_ce_bwd(const float* logits, int64_t ld, int R, int C, const int64_t* hard, const float* soft,
+                         int64_t ld_soft, const float* row_lse, const float* row_valid, const float* row_tsum,
+                         const float* denom, const float* gptr, float gscale, float* out32, void* out16, int out16_fmt,
+                         int64_t ld_out, int C_out, void* stream);
+int alpro_temp_grad(const float* dsa, const float* sa, int64_t na, const float* dsb, const float* sb, int64_t nb,
+                    const float* temp, float* dtemp, float coef, void* stream);
+int alpro_clamp_scalar(float* p, float lo, float hi, void* stream); /* temp.clamp_(0.001, 0.5), alpro_models.py:80-81 */
+int alpro_masked_mean_fwd(const float* x, int64_t seq_stride, int row0, const float* patch_mask, int B, int Np, int h,
+                          float* out, void* stream);
+int alpro_masked_mean_bwd(const float* dout, const float* patch_mask, int B, int Np, int h, float* dx, int64_t seq_stride,
+                          int row0, void* stream);
+int alpro_take_rows_fwd(const float* src, int R, int s0, int n, int L, int h, float* out32, void* out16, int fmt,
+                        void* stream);
+int alpro_take_rows_bwd(const float* dout, int R, int s0, int n, int L, int h, float* dsrc, void* stream);
+/* hard-negative sampling weights: softmax of the local sim block with -inf diagonal (alpro_models.py:288-299) */
+int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, float* w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
