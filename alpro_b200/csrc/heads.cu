@@ -301,6 +301,59 @@ __global__ void neg_weights_kernel(const float* __restrict__ sim, long long ld, 
   for (int c = lane; c < b; c += 32) w[r * b + c] = c == r ? 0.f : __expf(sim[r * ld + col0 + c] - mx) / s;
 }
 
+// out16 = dy * gelu'(pre)   (MLM transform backward, xbert.py:659-661)
+__global__ void gelu_grad_mul_kernel(const float* __restrict__ dy, const uint16_t* __restrict__ pre, int pre_fmt,
+                                     uint16_t* __restrict__ out, int out_fmt, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = f32_to_16(dy[i] * gelu_erf_grad(f16_to_32(pre[i], pre_fmt)), out_fmt);
+}
+
+// Prompter._compute_soft_labels (alpro_models.py:525-529): soft = softmax(sim) per row;
+// ignore = (argmax index < 0.2)  i.e. argmax == 0 (reference behaviour kept bug-compatible).
+__global__ void pseudo_labels_kernel(const float* __restrict__ sim, int C, float* __restrict__ soft,
+                                     uint8_t* __restrict__ ignore) {
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  const int r = blockIdx.x;
+  const float* x = sim + static_cast<long long>(r) * C;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    if (x[c] > mx) { mx = x[c]; arg = c; }
+  // block arg-max with first-index tie break (torch.max returns the first maximal index on CPU)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  if (lane == 0) { red[warp] = mx; redi[warp] = arg; }
+  __syncthreads();
+  if (warp == 0) {
+    float m2 = lane < nw ? red[lane] : -INFINITY;
+    int a2 = lane < nw ? redi[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m2, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, a2, o);
+      if (om > m2 || (om == m2 && oa < a2)) { m2 = om; a2 = oa; }
+    }
+    if (lane == 0) { red[0] = m2; redi[0] = a2; }
+  }
+  __syncthreads();
+  mx = red[0];
+  arg = redi[0];
+  __syncthreads();
+  float se = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += __expf(x[c] - mx);
+  se = block_sum(se, red);
+  const float inv = 1.f / se;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) soft[static_cast<long long>(r) * C + c] = __expf(x[c] - mx) * inv;
+  if (threadIdx.x == 0) ignore[r] = static_cast<float>(arg) < 0.2f ? 1 : 0;
+}
+
 inline int grid_for(long long work_items, int block) {
   long long g = cdiv(work_items, block);
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -440,5 +493,21 @@ extern "C" int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, 
   ALPRO_REQUIRE(sim && w && b > 0, "alpro_neg_weights: bad args");
   neg_weights_kernel<<<static_cast<unsigned>(cdiv(b, 4)), 128, 0, ST>>>(sim, ld, col0, b, w);
   ALPRO_CHECK_LAUNCH("alpro_neg_weights");
+  return 0;
+}
+
+extern "C" int alpro_gelu_grad_mul(const float* dy, const void* pre, int pre_fmt, void* out, int out_fmt, int64_t n,
+                                   void* stream) {
+  ALPRO_REQUIRE(dy && pre && out && n > 0, "alpro_gelu_grad_mul: bad args");
+  gelu_grad_mul_kernel<<<grid_for(n, 256), 256, 0, ST>>>(dy, static_cast<const uint16_t*>(pre), pre_fmt,
+                                                         static_cast<uint16_t*>(out), out_fmt, n);
+  ALPRO_CHECK_LAUNCH("alpro_gelu_grad_mul");
+  return 0;
+}
+
+extern "C" int alpro_pseudo_labels(const float* sim, int R, int C, float* soft, uint8_t* ignore, void* stream) {
+  ALPRO_REQUIRE(sim && soft && ignore && R > 0 && C > 0, "alpro_pseudo_labels: bad args");
+  pseudo_labels_kernel<<<R, 256, 0, ST>>>(sim, C, soft, ignore);
+  ALPRO_CHECK_LAUNCH("alpro_pseudo_labels");
   return 0;
 }

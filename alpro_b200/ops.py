@@ -294,3 +294,13 @@ def take_rows_bwd(dout, R, s0, n, L, h, dsrc):
 
 def neg_weights(sim, col0, b, w):
     check(_L.alpro_neg_weights(_p(sim), sim.stride(0), col0, b, _p(w), _s()), "alpro_neg_weights")
+
+
+def gelu_grad_mul(dy32, pre16, out16):
+    check(_L.alpro_gelu_grad_mul(_p(dy32), _p(pre16), _fmt(pre16), _p(out16), _fmt(out16), dy32.numel(), _s()),
+          "alpro_gelu_grad_mul")
+
+
+def pseudo_labels(sim, soft, ignore):
+    R, C = sim.shape
+    check(_L.alpro_pseudo_labels(_p(sim), R, C, _p(soft), _p(ignore), _s()), "alpro_pseudo_labels")

@@ -178,6 +178,10 @@ int alpro_masked_mean_bwd(const float* dout, const float* patch_mask, int B, int
 int alpro_take_rows_fwd(const float* src, int R, int s0, int n, int L, int h, float* out32, void* out16, int fmt,
                         void* stream);
 int alpro_take_rows_bwd(const float* dout, int R, int s0, int n, int L, int h, float* dsrc, void* stream);
+/* out16 = dy * gelu'(pre) (backward of BertPredictionHeadTransform's activation, xbert.py:659-661) */
+int alpro_gelu_grad_mul(const float* dy, const void* pre, int pre_fmt, void* out, int out_fmt, int64_t n, void* stream);
+/* Prompter._compute_soft_labels (alpro_models.py:525-529): soft = softmax(sim); ignore = (argmax index < 0.2) */
+int alpro_pseudo_labels(const float* sim, int R, int C, float* soft, uint8_t* ignore, void* stream);
 /* hard-negative sampling weights: softmax of the local sim block with -inf diagonal (alpro_models.py:288-299) */
 int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, float* w, void* stream);
 
