@@ -79,6 +79,31 @@ for _name, (_res, _args) in PROTOS.items():
     _fn.argtypes = _args
     globals()[_name] = _fn
 
+_NO_LAUNCH = {"alpro_last_error", "alpro_version", "alpro_num_sms"}
+
+
+class _Counting:
+    """Attribute proxy over the CDLL that counts kernel-launching C-ABI calls (bench.py reports it as gpu_launches)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.calls = 0
+        for name in PROTOS:
+            fn = getattr(cdll, name)
+            if name in _NO_LAUNCH:
+                setattr(self, name, fn)
+            else:
+                setattr(self, name, self._wrap(fn))
+
+    def _wrap(self, fn):
+        def call(*a):
+            self.calls += 1
+            return fn(*a)
+        return call
+
+
+counted = _Counting(lib)
+
 
 def check(rc, what=""):
     if rc != 0:

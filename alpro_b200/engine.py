@@ -495,7 +495,7 @@ class AlproEngine:
             self.t_visual = VisualEncoder("prompter.visual_encoder.model.", vis, dtype)
         self.sampler = multinomial_sampler
         self.comm = LocalComm()
-        self.launches = 0
+        self.last_grads = None
 
     # ------------------------------------------------------------------------------------------------ features
     def _proj_norm(self, P, x, ldx, wname, rows):
@@ -745,6 +745,7 @@ class AlproEngine:
         dx_text = self.bert.backward(P, self.W, ctx["tctx"], dte.view(nt * L, h), G, S)
         self.bert.embed_backward(P, ctx["ectx"], dx_text, G, S)
         self.visual.backward(P, self.W, ctx["vctx"], dve, G, S)
+        self.last_grads = G
         return G
 
     def _mlm_backward(self, P, ctx, G, gptr, dfo):

@@ -92,9 +92,8 @@ class _StepFn(torch.autograd.Function):
     (run_video_retrieval.py:432-442) populates `p.grad` of every nn.Parameter."""
 
     @staticmethod
-    def forward(ctx, model, batch, names, *params):
+    def forward(ctx, model, batch, names, need, *params):
         P = model._tensor_dict()
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         out, ectx = model.engine.forward(P, batch, need_grad=need)
         ctx.model, ctx.ectx, ctx.names = model, ectx, names
         ctx.loss_keys = [k for k in ("itc_loss", "itm_loss", "mlm_loss", "mpm_loss") if out.get(k) is not None]
@@ -115,7 +114,7 @@ class _StepFn(torch.autograd.Function):
         out = []
         for n in ctx.names:
             out.append(G[n] if n in G else None)
-        return (None, None, None) + tuple(out)
+        return (None, None, None, None) + tuple(out)
 
 
 class AlproBaseModel(nn.Module):
@@ -167,7 +166,8 @@ class AlproBaseModel(nn.Module):
                 continue
             names.append(n)
             params.append(p)
-        losses = _StepFn.apply(self, batch, names, *params)
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        losses = _StepFn.apply(self, batch, names, need, *params)
         out = dict(self._last_out)
         self._last_out = None
         keys = [k for k in ("itc_loss", "itm_loss", "mlm_loss", "mpm_loss") if out.get(k) is not None]

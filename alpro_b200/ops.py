@@ -12,6 +12,7 @@ KMAJOR, MNMAJOR = 0, 1
 ACT_NONE, ACT_GELU, ACT_GELU_GRAD, ACT_RELU, ACT_RELU_GRAD = 0, 1, 2, 3, 4
 
 _FMT = {torch.float16: F16, torch.bfloat16: BF16}
+GEMM_PROFILE = None  # set to a list to record (M, N, K, start_event, end_event) per GEMM launch (bench.py roofline)
 
 
 def _stream():
@@ -91,15 +92,23 @@ def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, a
     ep.skip_period = skip_period
     ep.split_k = split_k
     ep.alpha = alpha
-    check(_lib.alpro_gemm16(_ptr(a), _ptr(b), M, N, K, lda, ldb, a_layout, b_layout, _fmt(a), _fmt(b),
-                            ctypes.byref(ep), _stream()), "alpro_gemm16")
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.counted.alpro_gemm16(_ptr(a), _ptr(b), M, N, K, lda, ldb, a_layout, b_layout, _fmt(a), _fmt(b),
+                                    ctypes.byref(ep), _stream()), "alpro_gemm16")
+    if prof is not None:
+        e1.record()
+        prof.append((M, N, K, e0, e1))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # thin wrappers for the remaining entry points (argument order = include/alpro_b200.h)
 # ---------------------------------------------------------------------------------------------------------------------
 _KIND = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
-_L = _lib.lib
+_L = _lib.counted
 
 
 def _p(t):

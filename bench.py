@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — video-text pairs/sec for one ALPRO training step (forward + backward incl. the VTC feature exchange and
+the gradient all-reduce) on synthetic 8-frame 224^2 clips + 40-token captions (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                     CPU arm: the oracle port of the reference path on host cores
+
+Prints ONE JSON line (rank 0). `value` = whole-job pairs/s with inputs resident in HBM; `e2e` = the same metric through
+the reference-facing nn.Module call with HOST (pinned) batches, H2D copies and a D2H read of the losses inside the
+timed region. `roofline` describes the dominant kernel (gemm16_kernel, tensor bound); `cpu_baseline` is the oracle
+timed on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES, IMG, TXT_LEN, VOCAB, NUM_ENT = 8, 224, 40, 30522, 1000
+# algorithmic FLOPs per pair, BASELINE.md §2 (2*M*N*K per GEMM, 4*S*S*d per attention layer; no recompute/padding)
+FLOP_PER_PAIR = {"pretrain": 1846.9e9, "retrieval": 1375.7e9}
+
+
+def full_cfg(kind):
+    from oracle import configs
+    bert = dict(configs.BASE_BERT)
+    video = dict(configs.BASE_VIDEO)
+    video.update(num_frm=T_FRAMES, img_size=IMG)
+    vis = dict(d=768, depth=12, heads=12, T=T_FRAMES, img=IMG, patch=16)
+    return bert, video, vis
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16_tflops=p.get("bf16_tflops", 1590.0), sustained=p.get("bf16_tflops_sustained", 1400.0),
+                    hbm_gbs=p.get("hbm_gbs", 6650.0), source="measured")
+    return dict(bf16_tflops=1590.0, sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            parts = [x.strip() for x in l.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(kind, B, seed, device, pinned=False):
+    from alpro_b200 import synth
+    batch = synth.synth_batch(kind, B, T_FRAMES, IMG, TXT_LEN, VOCAB, seed=seed, num_entities=NUM_ENT)
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            out[k] = v.pin_memory() if pinned else v.to(device)
+        else:
+            out[k] = v
+    return out
+
+
+def batch_bytes(batch):
+    return sum(v.numel() * v.element_size() for v in batch.values() if torch.is_tensor(v))
+
+
+def build_model(kind, device, seed=0):
+    from alpro_b200 import modeling
+    bert, video, vis = full_cfg(kind)
+    bert = dict(bert)
+    bert["num_entities"] = NUM_ENT
+    cls = modeling.AlproForPretrain if kind == "pretrain" else modeling.AlproForVideoTextRetrieval
+    torch.manual_seed(seed)
+    model = cls(bert, video).to(device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():   # non-degenerate random weights (reference-style init leaves temporal_fc at zero)
+        for n, p in model.named_parameters():
+            leaf = n.split(".")[-1]
+            parent = n.split(".")[-2].lower() if "." in n else ""
+            if n.endswith("temp"):
+                p.fill_(0.07)
+            elif "norm" in parent:
+                p.copy_((1.0 if leaf == "weight" else 0.0) + 0.05 * torch.randn(p.shape, device=device, generator=g))
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, device=device, generator=g))
+    model.train()
+    return model
+
+
+def run_ours(args):
+    from alpro_b200 import comm as acomm, ops, _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    kind = args.workload
+    B = args.batch
+    model = build_model(kind, device)
+    if world > 1:
+        acomm.attach(model)
+    dev_batch = make_batch(kind, B, 1234 + rank, device)
+    host_batch = make_batch(kind, B, 1234 + rank, device, pinned=True)
+    h2d = batch_bytes(host_batch)
+
+    def step(batch):
+        out = model(batch)
+        loss = sum(v for k, v in out.items() if k.endswith("_loss") and v is not None)
+        loss.backward()
+        if world > 1:
+            acomm.allreduce_gradients(model)
+        for p in model.parameters():
+            p.grad = None
+        return out
+
+    def e2e_step():
+        b = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
+        out = step(b)
+        vals = torch.stack([out[k].detach() for k in out if k.endswith("_loss") and out[k] is not None])
+        return vals.cpu()   # D2H read of the step's result (synchronises)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_batch)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    calls0 = _lib.counted.calls
+    ms_step = timed(lambda: step(dev_batch), args.steps)
+    launches = (_lib.counted.calls - calls0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # roofline of the dominant kernel: event-timed GEMM launches of one extra step (tensor bound)
+    ops.GEMM_PROFILE = []
+    step(dev_batch)
+    torch.cuda.synchronize()
+    gemm_ms = sum(e0.elapsed_time(e1) for (_, _, _, e0, e1) in ops.GEMM_PROFILE)
+    gemm_flop = sum(2.0 * M * N * K for (M, N, K, _, _) in ops.GEMM_PROFILE)
+    n_gemm = len(ops.GEMM_PROFILE)
+    ops.GEMM_PROFILE = None
+    peaks = load_peaks()
+    achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pairs = B * world
+    value = pairs / (ms_step * 1e-3)
+    res = {
+        "metric": "video-text pairs/sec (fwd+bwd, 8x224^2)", "value": round(value, 3), "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 residual+statistics",
+        "data": "synthetic", "impl": "alpro_b200",
+        "config": {"workload": f"alpro_{kind}_step", "clips_per_gpu": B, "global_batch": pairs, "frames": T_FRAMES,
+                   "img": IMG, "txt_len": TXT_LEN, "parallelism": f"dp{world}", "l2": "inputs_exceed_l2",
+                   "losses": "VTC+VTM+MLM+PEM" if kind == "pretrain" else "VTC+VTM", "optimizer": "none (fwd+bwd+allreduce)"},
+        "tensor_frac_of_peak_whole_step": round(FLOP_PER_PAIR[kind] * value / world / (peaks["sustained"] * 1e12), 4),
+        "e2e": {"value": round(pairs / (ms_e2e * 1e-3), 3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 16 if kind == "pretrain" else 8, "ms_per_step": round(ms_e2e, 3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm16_kernel (tcgen05)", "achieved": round(achieved, 1),
+                     "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
+                     "peak_source": peaks["source"] + " (cuBLAS bf16 sustained)", "launches": n_gemm,
+                     "gemm_ms_per_step": round(gemm_ms, 3), "gemm_share_of_step": round(gemm_ms / ms_step, 3),
+                     "traffic": None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline(kind, steps=1)
+    print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(kind, steps=1, B=2):
+    """The oracle (CPU restatement of the reference path, pinned to the reference's golden vectors) on the host cores.
+    Bounded sample: B clips of the same workload (8x224^2, L=40, full-size model), fwd+bwd."""
+    from alpro_b200 import synth
+    from oracle import alpro_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bert, video, vis = full_cfg(kind)
+    spec = synth.model_spec(kind, bert, vis, NUM_ENT)
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for k, shp in spec.items():
+        c = synth.canonical_name(k)
+        if c in sd:
+            sd[k] = sd[c]
+        elif k.endswith("position_ids"):
+            sd[k] = torch.arange(shp[1]).unsqueeze(0)
+        elif k.endswith("temp"):
+            sd[k] = torch.tensor(0.07)
+        elif k.endswith("prompt_feat"):
+            sd[k] = torch.rand(shp, generator=g)
+        else:
+            sd[k] = 0.02 * torch.randn(shp, generator=g)
+            if "norm" in k.lower().split(".")[-2] and k.endswith("weight"):
+                sd[k] += 1.0
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.startswith("prompter."):
+            v.requires_grad_(True)
+    batch = synth.synth_batch(kind, B, T_FRAMES, IMG, TXT_LEN, VOCAB, seed=99, num_entities=NUM_ENT)
+    fwd = alpro_oracle.pretrain_forward if kind == "pretrain" else alpro_oracle.retrieval_forward
+    times = []
+    for _ in range(steps):
+        t0 = time.time()
+        out = fwd(sd, bert, vis, batch)
+        loss = sum(v for k, v in out.items() if k.endswith("_loss") and v is not None)
+        loss.backward()
+        times.append(time.time() - t0)
+        for v in sd.values():
+            v.grad = None
+    t = min(times)
+    return {"value": round(B / t, 4), "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{B} pairs (8x224^2 clips, L=40, full-size model), fwd+bwd, torch CPU fp32, best of {steps}",
+            "seconds": round(t, 2)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = args.workload
+    steps = max(1, min(args.steps, 3))
+    cb = cpu_baseline(kind, steps=steps)
+    res = {"impl": "reference", "metric": "video-text pairs/sec (fwd+bwd, 8x224^2)", "value": cb["value"],
+           "unit": "pairs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 0,
+           "ms_per_step": round(1e3 * 2 / cb["value"], 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"alpro_{kind}_step", "frames": T_FRAMES, "img": IMG, "txt_len": TXT_LEN,
+                      "note": "bounded sample of the same workload on host cores"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(res), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "retrieval"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when invoked directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
