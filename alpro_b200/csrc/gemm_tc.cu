@@ -115,8 +115,10 @@ __device__ __forceinline__ void store4_32(float* o, const float (&v)[4], bool fu
   }
 }
 
-// Epilogue for up to NR rows x 4 consecutive columns held by one lane on the coalesced side. All global loads of the
-// group are issued before any store so that they overlap (the compiler cannot hoist them itself: resid may alias out).
+// Epilogue for NR rows x 4 consecutive columns held by one lane on the coalesced side. All global loads of the group
+// are issued before any store so that they overlap (the compiler cannot hoist them itself: resid may alias out), and
+// the math is unconditional straight-line code (row indices are clamped for the loads, only the stores are predicated)
+// so that the NR*4 independent element chains interleave.
 template <int MODE, int NR>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[NR][4], const float4& b4,
                                               const long long (&row)[NR], const bool (&ok)[NR], int col) {
@@ -141,40 +143,58 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[N
   const bool has_out16 = (MODE == E_GENERIC || MODE == E_RESID_OUT32) ? (p.out16 != nullptr)
                                                                        : (MODE != E_OUT32);
   const bool has_out16b = (MODE == E_GENERIC) ? (p.out16b != nullptr) : (MODE == E_GELU_SAVE);
-  float u[NR][4];
-  if (act == ALPRO_ACT_GELU_GRAD || act == ALPRO_ACT_RELU_GRAD) {
+  long long lrow[NR];  // clamped row for loads (always in bounds)
 #pragma unroll
-    for (int i = 0; i < NR; ++i)
-      if (ok[i]) load4_16(p.aux16 + row[i] * p.ldaux + col, u[i], p.aux_fmt, full, ncol);
-  } else if (has_resid) {
+  for (int i = 0; i < NR; ++i) lrow[i] = ok[i] ? row[i] : static_cast<long long>(p.M) - 1;
+  float u[NR][4], rr[NR][4];
+  const bool grad_act = act == ALPRO_ACT_GELU_GRAD || act == ALPRO_ACT_RELU_GRAD;
+  if (grad_act) {
 #pragma unroll
-    for (int i = 0; i < NR; ++i)
-      if (ok[i]) load4_32(p.resid + row[i] * p.ldresid + col, u[i], full, ncol);
+    for (int i = 0; i < NR; ++i) load4_16(p.aux16 + lrow[i] * p.ldaux + col, u[i], p.aux_fmt, full, ncol);
+  }
+  if (has_resid) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) load4_32(p.resid + lrow[i] * p.ldresid + col, rr[i], full, ncol);
   }
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
-    if (!ok[i]) continue;
     v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w;
-    if (act == ALPRO_ACT_GELU || act == ALPRO_ACT_RELU) {
-      if (has_out16b) store4_16(p.out16b + row[i] * p.ld16b + col, v[i], p.out16b_fmt, full, ncol);
+  }
+  if (act == ALPRO_ACT_GELU || act == ALPRO_ACT_RELU) {
+    if (has_out16b) {
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if (ok[i]) store4_16(p.out16b + row[i] * p.ld16b + col, v[i], p.out16b_fmt, full, ncol);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[i][j] = act == ALPRO_ACT_GELU ? gelu_erf(v[i][j]) : fmaxf(v[i][j], 0.f);
-    } else if (act == ALPRO_ACT_GELU_GRAD) {
+  } else if (act == ALPRO_ACT_GELU_GRAD) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[i][j] *= gelu_erf_grad(u[i][j]);
-    } else if (act == ALPRO_ACT_RELU_GRAD) {
+  } else if (act == ALPRO_ACT_RELU_GRAD) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[i][j] = u[i][j] > 0.f ? v[i][j] : 0.f;
-    }
-    if (has_resid) {
-      if (MODE == E_GENERIC && (act == ALPRO_ACT_GELU_GRAD || act == ALPRO_ACT_RELU_GRAD))
-        load4_32(p.resid + row[i] * p.ldresid + col, u[i], full, ncol);  // rare combination: aux and resid
+  }
+  if (has_resid) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
       const bool skip = p.skip_period > 0 && (row[i] % p.skip_period) == 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = skip ? u[i][j] : v[i][j] + u[i][j];
+      for (int j = 0; j < 4; ++j) v[i][j] = skip ? rr[i][j] : v[i][j] + rr[i][j];
     }
-    if (has_out32) store4_32(p.out32 + row[i] * p.ld32 + col, v[i], full, ncol);
-    if (has_out16) store4_16(p.out16 + row[i] * p.ld16 + col, v[i], p.out16_fmt, full, ncol);
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    if (ok[i]) {
+      if (has_out32) store4_32(p.out32 + row[i] * p.ld32 + col, v[i], full, ncol);
+      if (has_out16) store4_16(p.out16 + row[i] * p.ld16 + col, v[i], p.out16_fmt, full, ncol);
+    }
   }
 }
 

@@ -138,7 +138,8 @@ __host__ __device__ inline uint32_t make_idesc_f16(int a_fmt, int b_fmt, int a_m
 // one MUFU.RCP and a degree-5 Horner — ~3x cheaper in the GEMM epilogue than libdevice erff.
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -153,17 +154,23 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// 16-bit storage helpers: fmt 0 = fp16, 1 = bf16
+// 16-bit storage helpers: fmt 0 = fp16, 1 = bf16. Branch-free (both conversions + select) so that the epilogues stay
+// straight-line code the scheduler can interleave across elements.
+__device__ __forceinline__ uint32_t pack2_16(float a, float b, int fmt) {
+  uint32_t h, bf;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));    // d.hi = first source, d.lo = second source
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(bf) : "f"(b), "f"(a));
+  return fmt ? bf : h;
+}
 __device__ __forceinline__ uint16_t f32_to_16(float v, int fmt) {
-  if (fmt == 0) return __half_as_ushort(__float2half_rn(v));
-  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  const uint16_t h = __half_as_ushort(__float2half_rn(v));
+  const uint16_t bf = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return fmt ? bf : h;
 }
 __device__ __forceinline__ float f16_to_32(uint16_t v, int fmt) {
-  if (fmt == 0) return __half2float(__ushort_as_half(v));
-  return __bfloat162float(__ushort_as_bfloat16(v));
-}
-__device__ __forceinline__ uint32_t pack2_16(float a, float b, int fmt) {
-  return static_cast<uint32_t>(f32_to_16(a, fmt)) | (static_cast<uint32_t>(f32_to_16(b, fmt)) << 16);
+  const float h = __half2float(__ushort_as_half(v));
+  const float bf = __uint_as_float(static_cast<uint32_t>(v) << 16);
+  return fmt ? bf : h;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -97,12 +97,17 @@ def test_matches_oracle_all_param_grads():
     out = model(to_cuda(batch))
     sum(v for k, v in out.items() if k.endswith("_loss") and v is not None).backward()
     bad = []
+    gmax = max(float(v.grad.abs().max()) for v in sd_g.values() if v.grad is not None)
     for n, p in model.named_parameters():
         if n.startswith("prompter.") or n.endswith("head.weight") and "visual_encoder" in n or n.endswith("head.bias") and "visual_encoder" in n:
             continue
         ref = sd_g[n].grad
         if ref is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        if float(ref.abs().max()) < 1e-6 * gmax:
+            # mathematically zero gradient (e.g. attention key bias: softmax is shift-invariant); only noise on both sides
+            assert float(p.grad.abs().max()) < 1e-4 * gmax, n
             continue
         e = helpers.rel_err(p.grad.cpu(), ref)
         if e > 3e-2:
