@@ -190,6 +190,14 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    if args.ncu:   # profiling aid: ncu --profile-from-start off ... python bench.py --ncu   (never a bench value)
+        step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     for _ in range(max(args.warmup, 3)):
         step(dev_batch)
     sampler = ClockSampler(local)
@@ -246,12 +254,28 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(kind, steps=1, B=2):
+def usable_cores(cap=32):
+    """Host threads the CPU arm may use: scheduler affinity, clipped by the cgroup CPU quota and by `cap` (torch's
+    intra-op scaling on this model is flat beyond ~32 threads; 128 oversubscribed threads ran 30x slower)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, cap))
+
+
+def cpu_baseline(kind, steps=1, B=1):
     """The oracle (CPU restatement of the reference path, pinned to the reference's golden vectors) on the host cores.
     Bounded sample: B clips of the same workload (8x224^2, L=40, full-size model), fwd+bwd."""
     from alpro_b200 import synth
     from oracle import alpro_oracle
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     bert, video, vis = full_cfg(kind)
     spec = synth.model_spec(kind, bert, vis, NUM_ENT)
@@ -319,6 +343,7 @@ def main():
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "retrieval"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="one warm step, then one step between cudaProfilerStart/Stop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
