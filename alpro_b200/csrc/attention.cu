@@ -206,19 +206,26 @@ __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int col) {
   return base + row * 128 + ((((col >> 3) ^ (row & 7)) << 4)) + ((col & 7) << 1);
 }
 
-// Cooperative gather of one [S_pad][64] tile (which: 0=q,1=k,2=v of qkv; or a plain [rows, ld] matrix with col offset).
+// Cooperative gather of one [S_pad][64] tile (q, k or v columns of qkv, or a plain [rows, ld] matrix) with 16-byte
+// cp.async copies: every thread keeps all of its copies in flight (no register staging), rows >= S are zero-filled
+// through the src-size operand. Completion: cp_async_wait_all() + __syncthreads().
 __device__ __forceinline__ void load_tile(const SAttnParams& p, const uint16_t* src, long long ld, int col0, int seq,
                                           int S_pad, uint8_t* smem_tile, const uint16_t* tok0_override) {
+  const uint32_t base = smem_u32(smem_tile);
   for (int idx = threadIdx.x; idx < S_pad * 8; idx += blockDim.x) {
     const int row = idx >> 3, ch = idx & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < p.S) {
-      const uint16_t* g = (row == 0 && tok0_override) ? tok0_override + ch * 8
-                                                       : src + srow(p, seq, row) * ld + col0 + ch * 8;
-      v = *reinterpret_cast<const uint4*>(g);
-    }
-    *reinterpret_cast<uint4*>(smem_tile + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+    const int rr = row < p.S ? row : 0;   // clamped (the copy reads 0 bytes for padded rows)
+    const uint16_t* g = (rr == 0 && tok0_override) ? tok0_override + ch * 8
+                                                    : src + srow(p, seq, rr) * ld + col0 + ch * 8;
+    const uint32_t nbytes = row < p.S ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + row * 128 + ((ch ^ (row & 7)) << 4)),
+                 "l"(g), "r"(nbytes)
+                 : "memory");
   }
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
   load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S_pad, sV, nullptr);
   for (int j = threadIdx.x; j < S_pad; j += blockDim.x)
     sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
+  cp_async_wait_all();
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -358,6 +366,7 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
     sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
     sLse[j] = j < p.S ? p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + j] : 0.f;
   }
+  cp_async_wait_all();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // token-0 upstream gradient scaling (mean over frames) applied in place, then D = rowsum(dO * O) recomputed as

@@ -93,67 +93,80 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += dy*xhat; dbeta += dy.
 // Each warp walks rows with a grid stride and keeps its dgamma/dbeta partials in registers; one block-level
 // reduction + fp32 atomics at the end.
-__global__ void layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, long long lddy,
+template <int NV4>
+__global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, long long lddy,
                                      const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, const float* __restrict__ gamma, long long M,
                                      int d, float* __restrict__ dx32, long long lddx, int accumulate,
                                      uint16_t* __restrict__ dx16, long long lddx16, int fmt, int zero_period,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float param_scale) {
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float param_scale,
+                                     float* __restrict__ colsum, int colsum_zero_period) {
   extern __shared__ float red[];  // [warps][d] x 2
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int nv = d >> 2;
-  float4 ag[LN_MAX_V4], ab[LN_MAX_V4];
+  float4 ag[NV4], ab[NV4], ac[NV4];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV4; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (long long row = static_cast<long long>(blockIdx.x) * nwarps + warp; row < M;
        row += static_cast<long long>(gridDim.x) * nwarps) {
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[LN_MAX_V4], g[LN_MAX_V4];
+    // Only the raw x / dy values stay live across the two passes (xhat and g = dy*gamma are recomputed) so that the
+    // kernel fits 2 blocks per SM next to its 3 x d/32 accumulator registers.
+    float4 xv[NV4], dv[NV4];
     float s1 = 0.f, s2 = 0.f;
+    float4* dxrow = reinterpret_cast<float4*>(dx32 + row * lddx);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV4; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
-        const float4 xv = reinterpret_cast<const float4*>(x + row * ldx)[c];
-        float4 dv;
+        if (accumulate) asm volatile("prefetch.global.L1 [%0];" ::"l"(dxrow + c));   // read-modify-write target
+        xv[i] = reinterpret_cast<const float4*>(x + row * ldx)[c];
         if (dy_kind == 0) {
-          dv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * lddy)[c];
+          dv[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * lddy)[c];
         } else {
           const uint2 w = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy) + row * lddy)[c];
-          dv.x = f16_to_32(static_cast<uint16_t>(w.x & 0xffff), dy_kind - 1);
-          dv.y = f16_to_32(static_cast<uint16_t>(w.x >> 16), dy_kind - 1);
-          dv.z = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), dy_kind - 1);
-          dv.w = f16_to_32(static_cast<uint16_t>(w.y >> 16), dy_kind - 1);
+          dv[i].x = f16_to_32(static_cast<uint16_t>(w.x & 0xffff), dy_kind - 1);
+          dv[i].y = f16_to_32(static_cast<uint16_t>(w.x >> 16), dy_kind - 1);
+          dv[i].z = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), dy_kind - 1);
+          dv[i].w = f16_to_32(static_cast<uint16_t>(w.y >> 16), dy_kind - 1);
         }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
-        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
-        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+        const float hx = (xv[i].x - mu) * rs, hy = (xv[i].y - mu) * rs, hz = (xv[i].z - mu) * rs, hw = (xv[i].w - mu) * rs;
+        const float gx = dv[i].x * gm.x, gy = dv[i].y * gm.y, gz = dv[i].z * gm.z, gw = dv[i].w * gm.w;
+        s1 += (gx + gy) + (gz + gw);
+        s2 += (gx * hx + gy * hy) + (gz * hz + gw * hw);
+        ag[i].x += dv[i].x * hx; ag[i].y += dv[i].y * hy; ag[i].z += dv[i].z * hz; ag[i].w += dv[i].w * hw;
+        ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
       }
     }
     const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
     const bool zero16 = zero_period > 0 && (row % zero_period) == 0;
+    const bool cs_on = colsum != nullptr && !(colsum_zero_period > 0 && (row % colsum_zero_period) == 0);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_V4; ++i) {
+    for (int i = 0; i < NV4; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
         float4 o;
-        o.x = rs * (g[i].x - c1 - xh[i].x * c2);
-        o.y = rs * (g[i].y - c1 - xh[i].y * c2);
-        o.z = rs * (g[i].z - c1 - xh[i].z * c2);
-        o.w = rs * (g[i].w - c1 - xh[i].w * c2);
-        float4* dst = reinterpret_cast<float4*>(dx32 + row * lddx) + c;
+        o.x = rs * (dv[i].x * gm.x - c1 - (xv[i].x - mu) * rs * c2);
+        o.y = rs * (dv[i].y * gm.y - c1 - (xv[i].y - mu) * rs * c2);
+        o.z = rs * (dv[i].z * gm.z - c1 - (xv[i].z - mu) * rs * c2);
+        o.w = rs * (dv[i].w * gm.w - c1 - (xv[i].w - mu) * rs * c2);
         if (accumulate) {
-          const float4 p = *dst;
-          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          const float4 pv = dxrow[c];
+          o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
         }
-        *dst = o;
+        dxrow[c] = o;
+        if (cs_on) { ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w; }
         if (dx16) {
           uint2 w;
           if (zero16) {
@@ -167,11 +180,26 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, l
       }
     }
   }
+  if (colsum) {   // bias gradient of the Linear whose output gradient this dx is (column sums of the new dx)
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) reinterpret_cast<float4*>(red + warp * d)[c] = ac[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float sc = 0.f;
+      for (int w = 0; w < nwarps; ++w) sc += red[w * d + c];
+      atomicAdd(colsum + c, sc * param_scale);
+    }
+    __syncthreads();
+  }
   if (!dgamma && !dbeta) return;
   float* rg = red;
   float* rb = red + nwarps * d;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
+  for (int i = 0; i < NV4; ++i) {
     const int c = lane + i * 32;
     if (c < nv) {
       reinterpret_cast<float4*>(rg + warp * d)[c] = ag[i];
@@ -191,20 +219,61 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, l
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// out[n] += alpha * sum_m x[m,n]   (bias gradients). grid = (ceil(N/256), row_chunks); 128 threads x 2 columns.
-__global__ void colsum16_kernel(const uint16_t* __restrict__ x, int fmt, long long ld, long long M, int N,
-                                float* __restrict__ out, float alpha, int zero_period) {
-  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (col >= N) return;
-  float s0 = 0.f, s1 = 0.f;
-  for (long long r = blockIdx.y; r < M; r += gridDim.y) {
-    if (zero_period > 0 && (r % zero_period) == 0) continue;
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(x + r * ld + col);
-    s0 += f16_to_32(static_cast<uint16_t>(w & 0xffff), fmt);
-    s1 += f16_to_32(static_cast<uint16_t>(w >> 16), fmt);
+// out[n] += alpha * sum_m x[m,n]   (bias gradients). Each warp streams whole rows slices with 128-bit loads (a warp
+// covers 256 columns of a row), 4 rows in flight; block = 8 warps on different rows, smem reduce, one atomic per column.
+__global__ void __launch_bounds__(256) colsum16_kernel(const uint16_t* __restrict__ x, int fmt, long long ld,
+                                                       long long M, int N, float* __restrict__ out, float alpha,
+                                                       int zero_period) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bool vec = (col + 8 <= N) && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (col < N) {
+    const long long stride = static_cast<long long>(gridDim.y) * 8;
+    for (long long r0 = static_cast<long long>(blockIdx.y) * 8 + warp; r0 < M; r0 += stride * 4) {
+      uint4 w[4];
+      bool use[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * stride;
+        use[u] = r < M && !(zero_period > 0 && (r % zero_period) == 0);
+        w[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (use[u]) {
+          if (vec) {
+            w[u] = *reinterpret_cast<const uint4*>(x + r * ld + col);
+          } else {
+            uint16_t t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (col + j < N) ? x[r * ld + col + j] : static_cast<uint16_t>(0);
+            w[u].x = t[0] | (static_cast<uint32_t>(t[1]) << 16); w[u].y = t[2] | (static_cast<uint32_t>(t[3]) << 16);
+            w[u].z = t[4] | (static_cast<uint32_t>(t[5]) << 16); w[u].w = t[6] | (static_cast<uint32_t>(t[7]) << 16);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += f16_to_32(static_cast<uint16_t>(ww[j] & 0xffff), fmt);
+          acc[2 * j + 1] += f16_to_32(static_cast<uint16_t>(ww[j] >> 16), fmt);
+        }
+      }
+    }
   }
-  atomicAdd(out + col, s0 * alpha);
-  if (col + 1 < N) atomicAdd(out + col + 1, s1 * alpha);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][c];
+    atomicAdd(out + blockIdx.x * 256 + c, s * alpha);
+  }
 }
 
 __global__ void colsum32_kernel(const float* __restrict__ x, long long ld, long long M, int N, float* __restrict__ out,
@@ -278,27 +347,28 @@ __global__ void vit_embed_fwd_kernel(const float* __restrict__ proj, const float
 }
 
 // Gradients of cls_token / pos_embed / time_embed: reductions of dx over (b,t), (b,n), b.
-// grid.x = 1 + N + T blocks, one output row each; threads over d; atomics not needed.
+// grid = (1 + N + T output rows, B): each block reduces its clip's rows for one output row and adds it with atomics
+// (outputs zero-initialised by the caller); threads over d.
 __global__ void vit_embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
                                      float* __restrict__ dtim, int B, int N, int T, int d, float alpha) {
   const int which = blockIdx.x;
+  const int b = blockIdx.y;
   const long long S = 1 + static_cast<long long>(N) * T;
+  const float* base = dx + b * S * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float s = 0.f;
     if (which == 0) {
-      for (int b = 0; b < B; ++b) s += dx[(b * S) * d + c];
-      dcls[c] = s * alpha;
-      dpos[c] = s * alpha;
+      s = base[c] * alpha;
+      atomicAdd(dcls + c, s);
+      atomicAdd(dpos + c, s);
     } else if (which <= N) {
       const int n = which - 1;
-      for (int b = 0; b < B; ++b)
-        for (int t = 0; t < T; ++t) s += dx[(b * S + 1 + static_cast<long long>(n) * T + t) * d + c];
-      dpos[static_cast<long long>(1 + n) * d + c] = s * alpha;
+      for (int t = 0; t < T; ++t) s += base[(1 + static_cast<long long>(n) * T + t) * d + c];
+      atomicAdd(dpos + static_cast<long long>(1 + n) * d + c, s * alpha);
     } else {
       const int t = which - 1 - N;
-      for (int b = 0; b < B; ++b)
-        for (int n = 0; n < N; ++n) s += dx[(b * S + 1 + static_cast<long long>(n) * T + t) * d + c];
-      dtim[static_cast<long long>(t) * d + c] = s * alpha;
+      for (int n = 0; n < N; ++n) s += base[(1 + static_cast<long long>(n) * T + t) * d + c];
+      atomicAdd(dtim + static_cast<long long>(t) * d + c, s * alpha);
     }
   }
 }
@@ -493,18 +563,25 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
                                    const float* mean, const float* rstd, const float* gamma, int64_t M, int d,
                                    float* dx32, int64_t lddx, int accumulate, void* dx16, int64_t lddx16,
                                    int dx16_fmt, int zero_period, float* dgamma, float* dbeta, float param_scale,
-                                   void* stream) {
+                                   float* colsum, int colsum_zero_period, void* stream) {
   ALPRO_REQUIRE(dy && x && mean && rstd && gamma && dx32 && M > 0, "alpro_layernorm_bwd: bad args");
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_bwd: d=%d unsupported", d);
   ALPRO_REQUIRE(dy_kind >= 0 && dy_kind <= 2, "alpro_layernorm_bwd: dy_kind");
-  const int wpb = 8;
+  const int wpb = 6;
   int grid = static_cast<int>(cdiv(M, wpb));
-  const int cap = num_sms() * 4;
+  const int cap = num_sms() * 2;   // one resident wave (2 blocks/SM): fewest same-address atomics at the end
   if (grid > cap) grid = cap;
   const size_t smem = static_cast<size_t>(2) * wpb * d * sizeof(float);
-  layernorm_bwd_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, accumulate, static_cast<uint16_t*>(dx16), lddx16,
-      dx16_fmt, zero_period, dgamma, dbeta, param_scale);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define ALPRO_LN_BWD(NV)                                                                                              \
+  layernorm_bwd_kernel<NV><<<grid, wpb * 32, smem, st>>>(dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, \
+                                                         accumulate, static_cast<uint16_t*>(dx16), lddx16, dx16_fmt,   \
+                                                         zero_period, dgamma, dbeta, param_scale, colsum,              \
+                                                         colsum_zero_period)
+  if (d <= 256) ALPRO_LN_BWD(2);
+  else if (d <= 768) ALPRO_LN_BWD(6);
+  else ALPRO_LN_BWD(8);
+#undef ALPRO_LN_BWD
   ALPRO_CHECK_LAUNCH("alpro_layernorm_bwd");
   return 0;
 }
@@ -518,9 +595,12 @@ extern "C" int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int 
     colsum32_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ld, M, N, out,
                                                                           alpha);
   } else {
-    ALPRO_REQUIRE(ld % 2 == 0, "alpro_colsum: ld must be even for 16-bit input");
-    dim3 grid(static_cast<unsigned>(cdiv(N, 256)), rows);
-    colsum16_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(x), kind - 1, ld,
+    int gy = static_cast<int>(cdiv(M, 8 * 16));   // >= 16 rows per warp
+    const int cap = (num_sms() * 8) / static_cast<int>(cdiv(N, 256));
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    dim3 grid(static_cast<unsigned>(cdiv(N, 256)), gy);
+    colsum16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(x), kind - 1, ld,
                                                                           M, N, out, alpha, zero_period);
   }
   ALPRO_CHECK_LAUNCH("alpro_colsum");
@@ -551,8 +631,8 @@ extern "C" int alpro_vit_embed_fwd(const float* proj, const float* cls, const fl
 extern "C" int alpro_vit_embed_bwd(const float* dx, float* dcls, float* dpos, float* dtim, int B, int N, int T, int d,
                                    float alpha, void* stream) {
   ALPRO_REQUIRE(dx && dcls && dpos && dtim, "alpro_vit_embed_bwd: bad args");
-  vit_embed_bwd_kernel<<<1 + N + T, 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, dcls, dpos, dtim, B, N, T, d,
-                                                                                 alpha);
+  vit_embed_bwd_kernel<<<dim3(1 + N + T, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, dcls, dpos, dtim, B, N,
+                                                                                          T, d, alpha);
   ALPRO_CHECK_LAUNCH("alpro_vit_embed_bwd");
   return 0;
 }

@@ -109,7 +109,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[N
   const bool has_out32 = (MODE == E_GENERIC) ? (p.out32 != nullptr) : (MODE == E_RESID_OUT32 || MODE == E_OUT32);
   const bool has_out16 = (MODE == E_GENERIC || MODE == E_RESID_OUT32) ? (p.out16 != nullptr)
                                                                        : (MODE != E_OUT32);
-  const bool has_out16b = (MODE == E_GENERIC) ? (p.out16b != nullptr) : (MODE == E_GELU_SAVE);
+  const bool has_out16b = (MODE == E_GENERIC || MODE == E_GELU_SAVE) ? (p.out16b != nullptr) : false;
   long long lrow[NR];  // clamped row for loads (always in bounds)
 #pragma unroll
   for (int i = 0; i < NR; ++i) lrow[i] = ok[i] ? row[i] : static_cast<long long>(p.M) - 1;
@@ -127,7 +127,19 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[N
   for (int i = 0; i < NR; ++i) {
     v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w;
   }
-  if (act == ALPRO_ACT_GELU || act == ALPRO_ACT_RELU) {
+  if (act == ALPRO_ACT_GELU) {
+    // out16b receives gelu'(pre) (NOT the pre-activation): the backward epilogue is then a plain multiply
+    float dv[NR][4];
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gelu_erf_both(v[i][j], v[i][j], dv[i][j]);
+    if (has_out16b) {
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if (ok[i]) store4_16(p.out16b + row[i] * p.ld16b + col, dv[i], p.out16b_fmt, full, ncol);
+    }
+  } else if (act == ALPRO_ACT_RELU) {
     if (has_out16b) {
 #pragma unroll
       for (int i = 0; i < NR; ++i)
@@ -136,12 +148,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[N
 #pragma unroll
     for (int i = 0; i < NR; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = act == ALPRO_ACT_GELU ? gelu_erf(v[i][j]) : fmaxf(v[i][j], 0.f);
+      for (int j = 0; j < 4; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
   } else if (act == ALPRO_ACT_GELU_GRAD) {
 #pragma unroll
     for (int i = 0; i < NR; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] *= gelu_erf_grad(u[i][j]);
+      for (int j = 0; j < 4; ++j) v[i][j] *= u[i][j];   // aux = gelu'(pre) saved by the forward epilogue
   } else if (act == ALPRO_ACT_RELU_GRAD) {
 #pragma unroll
     for (int i = 0; i < NR; ++i)

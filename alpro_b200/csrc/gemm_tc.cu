@@ -385,7 +385,7 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   int mode = E_GENERIC;
   if (p.split_k > 1) mode = E_ATOMIC;
   else if (p.act == ALPRO_ACT_NONE && !p.resid && !p.out32 && p.out16 && !p.out16b) mode = E_OUT16;
-  else if (p.act == ALPRO_ACT_GELU && !p.resid && !p.out32 && p.out16 && p.out16b) mode = E_GELU_SAVE;
+  else if (p.act == ALPRO_ACT_GELU && !p.resid && !p.out32 && p.out16) mode = E_GELU_SAVE;
   else if (p.act == ALPRO_ACT_GELU_GRAD && !p.resid && !p.out32 && p.out16 && !p.out16b) mode = E_GELU_GRAD;
   else if (p.act == ALPRO_ACT_NONE && p.resid && p.out32 && !p.out16b) mode = E_RESID_OUT32;
   else if (p.act == ALPRO_ACT_NONE && !p.resid && p.out32 && !p.out16 && !p.out16b) mode = E_OUT32;

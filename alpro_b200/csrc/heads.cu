@@ -301,12 +301,12 @@ __global__ void neg_weights_kernel(const float* __restrict__ sim, long long ld, 
   for (int c = lane; c < b; c += 32) w[r * b + c] = c == r ? 0.f : __expf(sim[r * ld + col0 + c] - mx) / s;
 }
 
-// out16 = dy * gelu'(pre)   (MLM transform backward, xbert.py:659-661)
+// out16 = dy * dact, dact = gelu'(pre) saved by the forward GEMM epilogue   (MLM transform backward, xbert.py:659-661)
 __global__ void gelu_grad_mul_kernel(const float* __restrict__ dy, const uint16_t* __restrict__ pre, int pre_fmt,
                                      uint16_t* __restrict__ out, int out_fmt, long long n) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    out[i] = f32_to_16(dy[i] * gelu_erf_grad(f16_to_32(pre[i], pre_fmt)), out_fmt);
+    out[i] = f32_to_16(dy[i] * f16_to_32(pre[i], pre_fmt), out_fmt);
 }
 
 // Prompter._compute_soft_labels (alpro_models.py:525-529): soft = softmax(sim) per row;

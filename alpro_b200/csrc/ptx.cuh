@@ -209,10 +209,26 @@ __device__ __forceinline__ float erf_fast(float x) {
   return copysignf(y, x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+// gelu(x) and gelu'(x) = Phi(x) + x*phi(x) from ONE exponential: exp(-(x/sqrt2)^2) of the erf formula is exp(-x^2/2).
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  const float z = x * 0.70710678118654752f;
+  const float az = fabsf(z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = __expf(-az * az);                 // = exp(-x^2/2)
+  const float erfv = copysignf(1.0f - poly * t * e, z);
+  const float cdf = 0.5f * (1.0f + erfv);
+  y = x * cdf;
+  dy = fmaf(x * 0.3989422804014327f, e, cdf);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float y, dy;
+  gelu_erf_both(x, y, dy);
+  return dy;
 }
 
 // 16-bit storage helpers: fmt 0 = fp16, 1 = bf16. Branch-free (both conversions + select) so that the epilogues stay

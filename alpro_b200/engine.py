@@ -249,8 +249,10 @@ class VisualEncoder:
         ops.temporal_pool_bwd(d_ve.contiguous(), dxn, B, N, T, d)
         dx = _empty((M, d), torch.float32, dev)
         dx16 = _empty((M, d), dt, dev)
+        last = f"{p}blocks.{self.depth - 1}."
         ops.layernorm_bwd(dxn, ctx["x_final"], ctx["st_f"][0], ctx["st_f"][1], P[p + "norm.weight"].detach(), dx, 0,
-                          dx16=dx16, dgamma=G[p + "norm.weight"], dbeta=G[p + "norm.bias"], param_scale=inv)
+                          dx16=dx16, dgamma=G[p + "norm.weight"], dbeta=G[p + "norm.bias"], param_scale=inv,
+                          colsum=G[last + "mlp.fc2.bias"])
         del dxn
         d4 = _empty((M, 4 * d), dt, dev)
         d3 = _empty((M, 3 * d), dt, dev)
@@ -258,10 +260,12 @@ class VisualEncoder:
         db_ = _empty((M, d), dt, dev)
         scratch = _empty((B * T, 3 * d), torch.float32, dev)
 
-        def wgrad(dy16, x16, wname, bname, zero_period=0):
+        def wgrad(dy16, x16, wname, bname=None, zero_period=0):
+            # bname=None: the bias gradient was already produced by the LayerNorm backward that emitted dy16
             ops.gemm16(dy16, x16, a_layout=MNMAJOR, b_layout=MNMAJOR, out32=G[wname].view(G[wname].shape[0], -1),
                        split_k=-1, alpha=inv)
-            ops.colsum(dy16, G[bname], inv, zero_period)
+            if bname is not None:
+                ops.colsum(dy16, G[bname], inv, zero_period)
 
         for i in reversed(range(self.depth)):
             b = f"{p}blocks.{i}."
@@ -270,32 +274,34 @@ class VisualEncoder:
             w = lambda n: W.get(b + n, P[b + n])
             # ---- MLP
             ops.gemm16(dx16, w("mlp.fc2.weight"), b_layout=MNMAJOR, act=ACT_GELU_GRAD, aux=c["pre"], out16=d4)
-            wgrad(dx16, c["hdn"], b + "mlp.fc2.weight", b + "mlp.fc2.bias")
+            wgrad(dx16, c["hdn"], b + "mlp.fc2.weight")
             ops.gemm16(d4, w("mlp.fc1.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d4, c["a_m"], b + "mlp.fc1.weight", b + "mlp.fc1.bias")
             ops.layernorm_bwd(da, c["x2"], c["st_m"][0], c["st_m"][1], g("norm2.weight"), dx, 1, dx16=dx16,
-                              dgamma=G[b + "norm2.weight"], dbeta=G[b + "norm2.bias"], param_scale=inv)
+                              dgamma=G[b + "norm2.weight"], dbeta=G[b + "norm2.bias"], param_scale=inv,
+                              colsum=G[b + "attn.proj.bias"])
             # ---- spatial attention
             ops.gemm16(dx16, w("attn.proj.weight"), b_layout=MNMAJOR, out16=da)          # d o_s
-            wgrad(dx16, c["o_s"], b + "attn.proj.weight", b + "attn.proj.bias")
+            wgrad(dx16, c["o_s"], b + "attn.proj.weight")
             ops.seq_attn_bwd(c["qkv_s"], None, c["lse"], da, d3, scratch, 1 + N, B * T, heads, T, T, Sc, scale)
             ops.gemm16(d3, w("attn.qkv.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d3, c["a_s"], b + "attn.qkv.weight", b + "attn.qkv.bias")
             # dx16 <- grad wrt x1 with cls rows zeroed (the temporal branch never touches cls rows)
             ops.layernorm_bwd(da, c["x1"], c["st_s"][0], c["st_s"][1], g("norm1.weight"), dx, 1, dx16=dx16,
                               zero_period=Sc, dgamma=G[b + "norm1.weight"], dbeta=G[b + "norm1.bias"],
-                              param_scale=inv)
+                              param_scale=inv, colsum=G[b + "temporal_fc.bias"], colsum_zero_period=Sc)
             # ---- temporal attention
             ops.gemm16(dx16, w("temporal_fc.weight"), b_layout=MNMAJOR, out16=da)        # d p_t
-            wgrad(dx16, c["p_t"], b + "temporal_fc.weight", b + "temporal_fc.bias")
+            wgrad(dx16, c["p_t"], b + "temporal_fc.weight")
             ops.gemm16(da, w("temporal_attn.proj.weight"), b_layout=MNMAJOR, out16=db_)  # d o_t
             wgrad(da, c["o_t"], b + "temporal_attn.proj.weight", b + "temporal_attn.proj.bias")
             ops.temporal_attn_bwd(c["qkv_t"], db_, d3, B, N, T, heads, scale)
             ops.gemm16(d3, w("temporal_attn.qkv.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d3, c["a_t"], b + "temporal_attn.qkv.weight", b + "temporal_attn.qkv.bias")
+            nxt = G[f"{p}blocks.{i - 1}.mlp.fc2.bias"] if i > 0 else G[p + "patch_embed.proj.bias"]
             ops.layernorm_bwd(da, c["x"], c["st_t"][0], c["st_t"][1], g("temporal_norm1.weight"), dx, 1, dx16=dx16,
                               dgamma=G[b + "temporal_norm1.weight"], dbeta=G[b + "temporal_norm1.bias"],
-                              param_scale=inv)
+                              param_scale=inv, colsum=nxt, colsum_zero_period=0 if i > 0 else Sc)
             ctx["blocks"][i] = None  # release saved activations
         # ---- embeddings (vit.py:324-361) and patch projection
         pos_idx, tim_idx = ctx["pos_idx"], ctx["tim_idx"]
@@ -309,7 +315,6 @@ class VisualEncoder:
             gtim.index_add_(0, tim_idx, dtim)
         ops.gemm16(dx16, ctx["patches"], a_layout=MNMAJOR, b_layout=MNMAJOR,
                    out32=G[p + "patch_embed.proj.weight"].view(d, -1), split_k=-1, alpha=inv)
-        ops.colsum(dx16, G[p + "patch_embed.proj.bias"], inv, Sc)
 
 
 # =====================================================================================================================
@@ -416,9 +421,10 @@ class BertEncoder:
         scale = 1.0 / math.sqrt(64)
         ff = self.cfg["intermediate_size"]
 
-        def wgrad(dy16, x16, gw, gb):
+        def wgrad(dy16, x16, gw, gb=None):
             ops.gemm16(dy16, x16, a_layout=MNMAJOR, b_layout=MNMAJOR, out32=gw, split_k=-1, alpha=inv)
-            ops.colsum(dy16, gb, inv)
+            if gb is not None:
+                ops.colsum(dy16, gb, inv)
 
         for c in reversed(ctx["layers"]):
             l = f"{self.p}bert.encoder.layer.{c['i']}."
@@ -428,10 +434,10 @@ class BertEncoder:
             dz2_16 = _empty((M, h), dt, dev)
             ops.layernorm_bwd(dy32, c["z2"], c["st2"][0], c["st2"][1], g("output.LayerNorm.weight"), dz2, 0,
                               dx16=dz2_16, dgamma=G[l + "output.LayerNorm.weight"],
-                              dbeta=G[l + "output.LayerNorm.bias"], param_scale=inv)
+                              dbeta=G[l + "output.LayerNorm.bias"], param_scale=inv, colsum=G[l + "output.dense.bias"])
             du = _empty((M, ff), dt, dev)
             ops.gemm16(dz2_16, w("output.dense.weight"), b_layout=MNMAJOR, act=ACT_GELU_GRAD, aux=c["pre"], out16=du)
-            wgrad(dz2_16, c["hdn"], G[l + "output.dense.weight"], G[l + "output.dense.bias"])
+            wgrad(dz2_16, c["hdn"], G[l + "output.dense.weight"])
             da32 = _empty((M, h), torch.float32, dev)
             ops.gemm16(du, w("intermediate.dense.weight"), b_layout=MNMAJOR, resid=dz2, out32=da32)
             wgrad(du, c["a16"], G[l + "intermediate.dense.weight"], G[l + "intermediate.dense.bias"])
@@ -439,10 +445,11 @@ class BertEncoder:
             dz1_16 = dz2_16
             ops.layernorm_bwd(da32, c["z1"], c["st1"][0], c["st1"][1], g("attention.output.LayerNorm.weight"), dz1, 0,
                               dx16=dz1_16, dgamma=G[l + "attention.output.LayerNorm.weight"],
-                              dbeta=G[l + "attention.output.LayerNorm.bias"], param_scale=inv)
+                              dbeta=G[l + "attention.output.LayerNorm.bias"], param_scale=inv,
+                              colsum=G[l + "attention.output.dense.bias"])
             dcx = _empty((M, h), dt, dev)
             ops.gemm16(dz1_16, w("attention.output.dense.weight"), b_layout=MNMAJOR, out16=dcx)
-            wgrad(dz1_16, c["cx"], G[l + "attention.output.dense.weight"], G[l + "attention.output.dense.bias"])
+            wgrad(dz1_16, c["cx"], G[l + "attention.output.dense.weight"])
             dqkv = _empty((M, 3 * h), dt, dev)
             ops.seq_attn_bwd(c["qkv"], ctx["mask"], c["lse"], dcx, dqkv, None, S_len, nseq, heads, 1, 1, S_len, scale)
             Wq, _ = self._qkv(P, W, l)

@@ -133,12 +133,13 @@ def layernorm_fwd(x, gamma, beta, eps, out32=None, out16=None, mean=None, rstd=N
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx32, accumulate, dx16=None, zero_period=0, dgamma=None, dbeta=None,
-                  param_scale=1.0):
+                  param_scale=1.0, colsum=None, colsum_zero_period=0):
     M, d = x.shape
     check(_L.alpro_layernorm_bwd(_p(dy), _KIND[dy.dtype], dy.stride(0), _p(x), x.stride(0), _p(mean), _p(rstd),
                                  _p(gamma), M, d, _p(dx32), dx32.stride(0), int(accumulate), _p(dx16),
                                  dx16.stride(0) if dx16 is not None else 0, _fmt(dx16) if dx16 is not None else 0,
-                                 zero_period, _p(dgamma), _p(dbeta), param_scale, _s()), "alpro_layernorm_bwd")
+                                 zero_period, _p(dgamma), _p(dbeta), param_scale, _p(colsum), colsum_zero_period,
+                                 _s()), "alpro_layernorm_bwd")
 
 
 def colsum(x, out, alpha=1.0, zero_period=0):

@@ -32,8 +32,8 @@ extern "C" {
 #define ALPRO_FMT_BF16 1
 
 #define ALPRO_ACT_NONE 0
-#define ALPRO_ACT_GELU 1      /* out = gelu_erf(acc + bias)                 (nn.GELU, vit.py:50,61; ACT2FN['gelu'] xbert.py:417) */
-#define ALPRO_ACT_GELU_GRAD 2 /* out = (acc) * gelu'(aux)                   (autograd of the above) */
+#define ALPRO_ACT_GELU 1      /* out = gelu_erf(acc + bias); out16b (optional) = gelu'(acc + bias)   (nn.GELU, vit.py:50,61; ACT2FN['gelu'] xbert.py:417) */
+#define ALPRO_ACT_GELU_GRAD 2 /* out = acc * aux, aux = the gelu' saved by ALPRO_ACT_GELU               (autograd of the above) */
 #define ALPRO_ACT_RELU 3
 #define ALPRO_ACT_RELU_GRAD 4 /* out = acc * (aux > 0) */
 
@@ -50,7 +50,7 @@ int alpro_num_sms(void);
  * Dense contraction on tcgen05 tensor cores (TMA-staged operands, TMEM fp32 accumulators, fused epilogue).
  *   acc[m,n] = sum_k A(m,k) * B(n,k)
  *   v        = alpha * acc + bias[n]
- *   act      : see ALPRO_ACT_*  (pre-activation v optionally saved to out16b for the backward pass)
+ *   act      : see ALPRO_ACT_*  (GELU: derivative gelu'(v) / RELU: pre-activation v optionally saved to out16b for the backward pass)
  *   v       += resid[m,n]       (fp32; rows with m % skip_period == 0 pass resid through unchanged when skip_period>0)
  *   out32[m,n] = v (fp32) and/or out16[m,n] = v (fmt out16_fmt)
  * Replaces F.linear / nn.Linear.forward on the path (vit.py:60,63,84,98,161; xbert.py:273-292,357,422,435,659,681) and
@@ -90,11 +90,13 @@ int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const f
                         float* out32, int64_t ld32, void* out16, int64_t ld16, int out16_fmt, float* mean, float* rstd,
                         void* stream);
 /* dy_kind 0 fp32 / 1 fp16 / 2 bf16. dx32 = (accumulate ? dx32 : 0) + LN'(dy); dx16 = 16-bit copy of the resulting dx32
- * (rows with row % zero_period == 0 written as zero when zero_period > 0). dgamma/dbeta += param_scale * sums (atomics). */
+ * (rows with row % zero_period == 0 written as zero when zero_period > 0). dgamma/dbeta += param_scale * sums (atomics).
+ * colsum (optional) += param_scale * column sums of the resulting dx over rows with row % colsum_zero_period != 0: the
+ * bias gradient of the Linear layer whose output gradient this dx is (saves a separate pass over dx). */
 int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, const float* x, int64_t ldx, const float* mean,
                         const float* rstd, const float* gamma, int64_t M, int d, float* dx32, int64_t lddx,
                         int accumulate, void* dx16, int64_t lddx16, int dx16_fmt, int zero_period, float* dgamma,
-                        float* dbeta, float param_scale, void* stream);
+                        float* dbeta, float param_scale, float* colsum, int colsum_zero_period, void* stream);
 /* out[n] += alpha * sum_m x[m,n]; kind 0 fp32 / 1 fp16 / 2 bf16 (bias gradients of every nn.Linear on the path) */
 int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int N, float* out, float alpha, int zero_period,
                  void* stream);
@@ -178,8 +180,9 @@ int alpro_masked_mean_bwd(const float* dout, const float* patch_mask, int B, int
 int alpro_take_rows_fwd(const float* src, int R, int s0, int n, int L, int h, float* out32, void* out16, int fmt,
                         void* stream);
 int alpro_take_rows_bwd(const float* dout, int R, int s0, int n, int L, int h, float* dsrc, void* stream);
-/* out16 = dy * gelu'(pre) (backward of BertPredictionHeadTransform's activation, xbert.py:659-661) */
-int alpro_gelu_grad_mul(const float* dy, const void* pre, int pre_fmt, void* out, int out_fmt, int64_t n, void* stream);
+/* out16 = dy * dact, dact = the activation derivative saved by an ALPRO_ACT_GELU epilogue (backward of
+ * BertPredictionHeadTransform's activation, xbert.py:659-661) */
+int alpro_gelu_grad_mul(const float* dy, const void* dact, int dact_fmt, void* out, int out_fmt, int64_t n, void* stream);
 /* Prompter._compute_soft_labels (alpro_models.py:525-529): soft = softmax(sim); ignore = (argmax index < 0.2) */
 int alpro_pseudo_labels(const float* sim, int R, int C, float* soft, uint8_t* ignore, void* stream);
 /* hard-negative sampling weights: softmax of the local sim block with -inf diagonal (alpro_models.py:288-299) */
