@@ -30,47 +30,83 @@ struct TAttnParams {
   float scale;
 };
 
-template <int T>
-__device__ __forceinline__ void tattn_load(const TAttnParams& p, long long row0, int head, int lane, float (&q)[T][2],
-                                           float (&k)[T][2], float (&v)[T][2]) {
+// Lane mapping: lane = (i, part) with i = query/frame index (T of them) and `part` one of 32/T slices of the 64 head
+// dims. A lane holds q_i[slice] and k_j[slice], v_j[slice] for all j, so every score needs only log2(32/T) shuffles
+// (16 per warp for T=8) and the PV product is lane-local.
+template <int DPP>
+__device__ __forceinline__ void ld16(const uint16_t* ptr, float (&out)[DPP], int fmt) {
+  uint32_t w[DPP / 2];
+  if (DPP == 16) {
+    const uint4 a = *reinterpret_cast<const uint4*>(ptr);
+    const uint4 b = *reinterpret_cast<const uint4*>(ptr + 8);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4 % (DPP / 2)] = b.x; w[5 % (DPP / 2)] = b.y; w[6 % (DPP / 2)] = b.z; w[7 % (DPP / 2)] = b.w;
+  } else if (DPP == 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(ptr);
+    w[0] = a.x; w[1 % (DPP / 2)] = a.y; w[2 % (DPP / 2)] = a.z; w[3 % (DPP / 2)] = a.w;
+  } else if (DPP == 4) {
+    const uint2 a = *reinterpret_cast<const uint2*>(ptr);
+    w[0] = a.x; w[1 % (DPP / 2)] = a.y;
+  } else {
+    w[0] = *reinterpret_cast<const uint32_t*>(ptr);
+  }
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const uint16_t* base = p.qkv + (row0 + t) * p.ld_qkv + head * DH + lane * 2;
-    const uint32_t wq = *reinterpret_cast<const uint32_t*>(base);
-    const uint32_t wk = *reinterpret_cast<const uint32_t*>(base + p.d);
-    const uint32_t wv = *reinterpret_cast<const uint32_t*>(base + 2 * p.d);
-    q[t][0] = f16_to_32(wq & 0xffff, p.fmt); q[t][1] = f16_to_32(wq >> 16, p.fmt);
-    k[t][0] = f16_to_32(wk & 0xffff, p.fmt); k[t][1] = f16_to_32(wk >> 16, p.fmt);
-    v[t][0] = f16_to_32(wv & 0xffff, p.fmt); v[t][1] = f16_to_32(wv >> 16, p.fmt);
+  for (int j = 0; j < DPP / 2; ++j) {
+    out[2 * j] = f16_to_32(static_cast<uint16_t>(w[j] & 0xffff), fmt);
+    out[2 * j + 1] = f16_to_32(static_cast<uint16_t>(w[j] >> 16), fmt);
   }
 }
-
-template <int T>
-__device__ __forceinline__ void tattn_probs(const float (&q)[T][2], const float (&k)[T][2], float scale,
-                                            float (&pr)[T][T]) {
+template <int DPP>
+__device__ __forceinline__ void st16(uint16_t* ptr, const float (&v)[DPP], int fmt) {
+  uint32_t w[DPP / 2];
 #pragma unroll
-  for (int i = 0; i < T; ++i) {
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < T; ++j) {
-      pr[i][j] = warp_sum(q[i][0] * k[j][0] + q[i][1] * k[j][1]) * scale;
-      mx = fmaxf(mx, pr[i][j]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < T; ++j) {
-      pr[i][j] = __expf(pr[i][j] - mx);
-      sum += pr[i][j];
-    }
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int j = 0; j < T; ++j) pr[i][j] *= inv;
+  for (int j = 0; j < DPP / 2; ++j) w[j] = pack2_16(v[2 * j], v[2 * j + 1], fmt);
+  if (DPP == 16) {
+    *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(ptr + 8) = make_uint4(w[4 % (DPP / 2)], w[5 % (DPP / 2)], w[6 % (DPP / 2)], w[7 % (DPP / 2)]);
+  } else if (DPP == 8) {
+    *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1 % (DPP / 2)], w[2 % (DPP / 2)], w[3 % (DPP / 2)]);
+  } else if (DPP == 4) {
+    *reinterpret_cast<uint2*>(ptr) = make_uint2(w[0], w[1 % (DPP / 2)]);
+  } else {
+    *reinterpret_cast<uint32_t*>(ptr) = w[0];
   }
 }
+template <int PARTS>
+__device__ __forceinline__ float part_sum(float v) {
+#pragma unroll
+  for (int o = PARTS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-// grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by warp (n==0,head).
+// scores + softmax for this lane's query row i (identical in all PARTS lanes of the row)
+template <int T, int DPP, int PARTS>
+__device__ __forceinline__ void tattn_row_probs(const float (&q)[DPP], const float (&k)[T][DPP], float scale,
+                                                float (&pr)[T]) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < DPP; ++e) s += q[e] * k[j][e];
+    pr[j] = part_sum<PARTS>(s) * scale;
+    mx = fmaxf(mx, pr[j]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    pr[j] = __expf(pr[j] - mx);
+    sum += pr[j];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int j = 0; j < T; ++j) pr[j] *= inv;
+}
+
+// grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by the n==0 warps.
 template <int T>
 __global__ void tattn_fwd_kernel(const TAttnParams p) {
+  constexpr int PARTS = 32 / T, DPP = DH / PARTS;
   const int lane = threadIdx.x & 31;
   const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = static_cast<long long>(p.B) * p.N * p.heads;
@@ -82,25 +118,34 @@ __global__ void tattn_fwd_kernel(const TAttnParams p) {
   const long long clip_rows = 1 + static_cast<long long>(p.N) * T;
   const long long row0 = b * clip_rows + 1 + static_cast<long long>(n) * T;
   if (n == 0) *reinterpret_cast<uint32_t*>(p.out + b * clip_rows * p.ld_out + head * DH + lane * 2) = 0u;  // cls row
-  float q[T][2], k[T][2], v[T][2], pr[T][T];
-  tattn_load<T>(p, row0, head, lane, q, k, v);
-  tattn_probs<T>(q, k, p.scale, pr);
+  const int i = lane / PARTS, part = lane % PARTS;
+  const int coff = head * DH + part * DPP;
+  float q[DPP], k[T][DPP], v[T][DPP], pr[T];
+  ld16<DPP>(p.qkv + (row0 + i) * p.ld_qkv + coff, q, p.fmt);
 #pragma unroll
-  for (int i = 0; i < T; ++i) {
-    float o0 = 0.f, o1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < T; ++j) {
-      o0 += pr[i][j] * v[j][0];
-      o1 += pr[i][j] * v[j][1];
-    }
-    *reinterpret_cast<uint32_t*>(p.out + (row0 + i) * p.ld_out + head * DH + lane * 2) = pack2_16(o0, o1, p.fmt);
+  for (int j = 0; j < T; ++j) {
+    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, k[j], p.fmt);
+    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + 2 * p.d + coff, v[j], p.fmt);
   }
+  tattn_row_probs<T, DPP, PARTS>(q, k, p.scale, pr);
+  float o[DPP];
+#pragma unroll
+  for (int e = 0; e < DPP; ++e) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < T; ++j) a += pr[j] * v[j][e];
+    o[e] = a;
+  }
+  st16<DPP>(p.out + (row0 + i) * p.ld_out + coff, o, p.fmt);
 }
 
 template <int T>
 __global__ void tattn_bwd_kernel(const TAttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int PARTS = 32 / T, DPP = DH / PARTS;
+  constexpr int WPB = 4;
+  __shared__ float sQ[WPB][T][DH], sG[WPB][T][DH], sP[WPB][T][T], sDS[WPB][T][T];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wib;
   const long long total = static_cast<long long>(p.B) * p.N * p.heads;
   if (unit >= total) return;
   const int head = static_cast<int>(unit % p.heads);
@@ -115,43 +160,80 @@ __global__ void tattn_bwd_kernel(const TAttnParams p) {
     *reinterpret_cast<uint32_t*>(z + p.d) = 0u;
     *reinterpret_cast<uint32_t*>(z + 2 * p.d) = 0u;
   }
-  float q[T][2], k[T][2], v[T][2], pr[T][T], go[T][2];
-  tattn_load<T>(p, row0, head, lane, q, k, v);
-  tattn_probs<T>(q, k, p.scale, pr);
+  const int i = lane / PARTS, part = lane % PARTS;
+  const int coff = head * DH + part * DPP;
+  // k_j / v_j slices are streamed (re-read from L1) instead of being held: 2*T*DPP floats would not fit the register file
+  float q[DPP], go[DPP], pr[T];
+  ld16<DPP>(p.qkv + (row0 + i) * p.ld_qkv + coff, q, p.fmt);
+  ld16<DPP>(p.dout + (row0 + i) * p.ld_dout + coff, go, p.fmt);
+  float mx = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(p.dout + (row0 + t) * p.ld_dout + head * DH + lane * 2);
-    go[t][0] = f16_to_32(w & 0xffff, p.fmt);
-    go[t][1] = f16_to_32(w >> 16, p.fmt);
+  for (int j = 0; j < T; ++j) {
+    float kj[DPP];
+    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, kj, p.fmt);
+    float sdot = 0.f;
+#pragma unroll
+    for (int e = 0; e < DPP; ++e) sdot += q[e] * kj[e];
+    pr[j] = part_sum<PARTS>(sdot) * p.scale;
+    mx = fmaxf(mx, pr[j]);
   }
-  float dq[T][2], dk[T][2], dv[T][2];
+  float sum = 0.f;
 #pragma unroll
-  for (int t = 0; t < T; ++t) dq[t][0] = dq[t][1] = dk[t][0] = dk[t][1] = dv[t][0] = dv[t][1] = 0.f;
+  for (int j = 0; j < T; ++j) {
+    pr[j] = __expf(pr[j] - mx);
+    sum += pr[j];
+  }
+  const float invs = 1.f / sum;
+  float dp[T], dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < T; ++i) {
-    float dp[T];
-    float dot = 0.f;
+  for (int j = 0; j < T; ++j) {
+    pr[j] *= invs;
+    float vj[DPP];
+    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + 2 * p.d + coff, vj, p.fmt);
+    float sdot = 0.f;
 #pragma unroll
-    for (int j = 0; j < T; ++j) {
-      dp[j] = warp_sum(go[i][0] * v[j][0] + go[i][1] * v[j][1]);
-      dot += dp[j] * pr[i][j];
-      dv[j][0] += pr[i][j] * go[i][0];
-      dv[j][1] += pr[i][j] * go[i][1];
+    for (int e = 0; e < DPP; ++e) sdot += go[e] * vj[e];
+    dp[j] = part_sum<PARTS>(sdot);
+    dot += dp[j] * pr[j];
+  }
+  float dq[DPP];
+#pragma unroll
+  for (int e = 0; e < DPP; ++e) dq[e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const float ds = pr[j] * (dp[j] - dot) * p.scale;
+    if (part == 0) {
+      sP[wib][i][j] = pr[j];
+      sDS[wib][i][j] = ds;
     }
+    float kj[DPP];
+    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, kj, p.fmt);
 #pragma unroll
-    for (int j = 0; j < T; ++j) {
-      const float ds = pr[i][j] * (dp[j] - dot) * p.scale;
-      dq[i][0] += ds * k[j][0]; dq[i][1] += ds * k[j][1];
-      dk[j][0] += ds * q[i][0]; dk[j][1] += ds * q[i][1];
+    for (int e = 0; e < DPP; ++e) dq[e] += ds * kj[e];
+  }
+#pragma unroll
+  for (int e = 0; e < DPP; ++e) {
+    sQ[wib][i][part * DPP + e] = q[e];
+    sG[wib][i][part * DPP + e] = go[e];
+  }
+  uint16_t* o = p.out + (row0 + i) * p.ld_out + coff;
+  st16<DPP>(o, dq, p.fmt);
+  __syncwarp();
+  // role switch: this lane now owns key/value row j = i
+  float dk[DPP], dv[DPP];
+#pragma unroll
+  for (int e = 0; e < DPP; ++e) dk[e] = dv[e] = 0.f;
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    const float ds = sDS[wib][r][i], pp = sP[wib][r][i];
+#pragma unroll
+    for (int e = 0; e < DPP; ++e) {
+      dk[e] += ds * sQ[wib][r][part * DPP + e];
+      dv[e] += pp * sG[wib][r][part * DPP + e];
     }
   }
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    uint16_t* o = p.out + (row0 + t) * p.ld_out + head * DH + lane * 2;
-    *reinterpret_cast<uint32_t*>(o) = pack2_16(dq[t][0], dq[t][1], p.fmt);
-    *reinterpret_cast<uint32_t*>(o + p.d) = pack2_16(dk[t][0], dk[t][1], p.fmt);
-    *reinterpret_cast<uint32_t*>(o + 2 * p.d) = pack2_16(dv[t][0], dv[t][1], p.fmt);
-  }
+  st16<DPP>(o + p.d, dk, p.fmt);
+  st16<DPP>(o + 2 * p.d, dv, p.fmt);
 }
 
 // ================================================================================================ sequence attention

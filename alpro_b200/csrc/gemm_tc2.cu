@@ -177,6 +177,28 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int tile = w / p.split_k;
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile - m_blk * p.num_n_tiles;
+      if (MODE == E_GELU_GRAD) {   // same idea for the saved activation derivative (16-bit, 256 B per row-half)
+        const long long prow = static_cast<long long>(m_blk) * (2 * BM) + cta_rank * BM + q * 32 + lane;
+        const int pcol = n_blk * BN + half * (BN / 2);
+        if (prow < p.M) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (pcol + j * 64 < p.N)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux16 + prow * p.ldaux + pcol + j * 64));
+        }
+      }
+      if (MODE == E_RESID_OUT32 || (MODE == E_GENERIC && p.resid)) {
+        // While the MMAs of this tile are still running, pull this warp's residual rows towards L2 so that the
+        // epilogue's fp32 residual loads are not exposed DRAM latency.
+        const long long prow = static_cast<long long>(m_blk) * (2 * BM) + cta_rank * BM + q * 32 + lane;
+        const int pcol = n_blk * BN + half * (BN / 2);
+        if (prow < p.M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (pcol + j * 32 < p.N)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + prow * p.ldresid + pcol + j * 32));
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const long long row0 = static_cast<long long>(m_blk) * (2 * BM) + cta_rank * BM + q * 32;
@@ -212,20 +234,19 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (col + 3 < p.N) b4.w = __ldg(p.bias + col + 3);
             }
           }
+          {
+            float v[8][4];
+            long long rows[8];
+            bool ok[8];
 #pragma unroll
-          for (int i0 = 0; i0 < 8; i0 += 4) {
-            float v[4][4];
-            long long rows[4];
-            bool ok[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rl = crow + 4 * (i0 + i);
+            for (int i = 0; i < 8; ++i) {
+              const int rl = crow + 4 * i;
               rows[i] = row0 + rl;
               ok[i] = rows[i] < p.M;
               const float4 t = *reinterpret_cast<const float4*>(stg + rl * EPI_CHUNK + ((cch ^ (rl & 7)) << 2));
               v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
             }
-            epilogue_rows<MODE, 4>(p, v, b4, rows, ok, col);
+            epilogue_rows<MODE, 8>(p, v, b4, rows, ok, col);   // all 8 rows at once: 8 global loads in flight per lane
           }
         }
         __syncwarp();
