@@ -20,6 +20,12 @@ namespace {
 constexpr int DH = 64;
 constexpr float LOG2E = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2(float x) {   // single MUFU.EX2 (ex2() adds range/denormal fix-up code)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ================================================================================================ temporal attention
 struct TAttnParams {
   const uint16_t* qkv;  // [rows, 3*d]
@@ -105,7 +111,7 @@ __device__ __forceinline__ void tattn_row_probs(const float (&q)[DPP], const flo
 
 // grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by the n==0 warps.
 template <int T>
-__global__ void tattn_fwd_kernel(const TAttnParams p) {
+__global__ void __launch_bounds__(128, 4) tattn_fwd_kernel(const TAttnParams p) {
   constexpr int PARTS = 32 / T, DPP = DH / PARTS;
   const int lane = threadIdx.x & 31;
   const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -140,7 +146,7 @@ __global__ void tattn_fwd_kernel(const TAttnParams p) {
 }
 
 template <int T>
-__global__ void tattn_bwd_kernel(const TAttnParams p) {
+__global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) {
   constexpr int PARTS = 32 / T, DPP = DH / PARTS;
   constexpr int WPB = 4;
   __shared__ float sQ[WPB][T][DH], sG[WPB][T][DH], sP[WPB][T][T], sDS[WPB][T][T];
@@ -311,8 +317,9 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// grid (heads, nseq), 128 threads. NT_MAX = max number of 8-key tiles (S_pad / 8).
-template <bool BF, int NT_MAX>
+// grid (heads, nseq), 128 threads. NT = number of 8-key tiles; EXACT = NT is the true tile count (no predication),
+// otherwise NT is an upper bound and the loops are predicated on the runtime count.
+template <bool BF, int NT, bool EXACT>
 __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
   extern __shared__ __align__(128) uint8_t sm[];
   const int head = blockIdx.x, seq = blockIdx.y;
@@ -331,25 +338,35 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV);
-  const int nt = S_pad >> 3;
+  const int nt = EXACT ? NT : (S_pad >> 3);
   const float sl2 = p.scale * LOG2E;
+  // Per-lane ldmatrix address pieces. Every fragment row index is (lane & 7) + multiples of 8, so the swizzle term
+  // (chunk ^ (row & 7)) depends only on the lane and the 16-byte chunk -> four precomputed byte offsets per pattern.
+  const int l7 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
+  uint32_t xa[4], xb[4];   // chunk = 2*i + b4 (A operands / transposed B)   and   chunk = 2*i + b3 (plain B operands)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xa[i] = static_cast<uint32_t>(((2 * i + b4) ^ l7) << 4);
+    xb[i] = static_cast<uint32_t>(((2 * i + b3) ^ l7) << 4);
+  }
+  const uint32_t q_lane = smem_u32(sQ) + (l7 + b3 * 8) * 128;   // + qt*2048 + xa[ks]
+  const uint32_t k_lane = smem_u32(sK) + (l7 + b4 * 8) * 128;   // + n2*2048 + xb[ks]
+  const uint32_t v_lane = smem_u32(sV) + (l7 + b3 * 8) * 128;   // + kk*2048 + xa[dp]
 
   for (int qt = warp; qt < (S_pad >> 4); qt += 4) {
     uint32_t qa[4][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-      ldsm_x4(qa[ks], tile_addr(q_base, qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 16 + (lane >> 4) * 8));
-    float s[NT_MAX][4];
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(qa[ks], q_lane + qt * 2048 + xa[ks]);
+    float s[NT][4];
 #pragma unroll
-    for (int n2 = 0; n2 < NT_MAX / 2; ++n2) {
-      if (n2 * 2 < nt) {
+    for (int n2 = 0; n2 < NT / 2; ++n2) {
+      if (EXACT || n2 * 2 < nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) s[2 * n2][e] = s[2 * n2 + 1][e] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           uint32_t kb[4];
-          ldsm_x4(kb, tile_addr(k_base, n2 * 16 + (lane & 7) + (lane >> 4) * 8, ks * 16 + ((lane >> 3) & 1) * 8));
+          ldsm_x4(kb, k_lane + n2 * 2048 + xb[ks]);
           mma16816<BF>(s[2 * n2], qa[ks], kb[0], kb[1]);
           mma16816<BF>(s[2 * n2 + 1], qa[ks], kb[2], kb[3]);
         }
@@ -358,11 +375,11 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
     // softmax over keys (rows g and g+8 of this query tile), base-2 domain
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int n = 0; n < NT_MAX; ++n) {
-      if (n < nt) {
-        const float mk0 = sMask[n * 8 + 2 * t], mk1 = sMask[n * 8 + 2 * t + 1];
-        s[n][0] = s[n][0] * sl2 + mk0; s[n][1] = s[n][1] * sl2 + mk1;
-        s[n][2] = s[n][2] * sl2 + mk0; s[n][3] = s[n][3] * sl2 + mk1;
+    for (int n = 0; n < NT; ++n) {
+      if (EXACT || n < nt) {
+        const float2 mk = *reinterpret_cast<const float2*>(sMask + n * 8 + 2 * t);
+        s[n][0] = fmaf(s[n][0], sl2, mk.x); s[n][1] = fmaf(s[n][1], sl2, mk.y);
+        s[n][2] = fmaf(s[n][2], sl2, mk.x); s[n][3] = fmaf(s[n][3], sl2, mk.y);
         m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
         m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
       }
@@ -371,10 +388,10 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int n = 0; n < NT_MAX; ++n) {
-      if (n < nt) {
-        s[n][0] = exp2f(s[n][0] - m0); s[n][1] = exp2f(s[n][1] - m0);
-        s[n][2] = exp2f(s[n][2] - m1); s[n][3] = exp2f(s[n][3] - m1);
+    for (int n = 0; n < NT; ++n) {
+      if (EXACT || n < nt) {
+        s[n][0] = ex2(s[n][0] - m0); s[n][1] = ex2(s[n][1] - m0);
+        s[n][2] = ex2(s[n][2] - m1); s[n][3] = ex2(s[n][3] - m1);
         l0 += s[n][0] + s[n][1];
         l1 += s[n][2] + s[n][3];
       }
@@ -388,8 +405,8 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < NT_MAX / 2; ++kk) {
-      if (kk * 2 < nt) {
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      if (EXACT || kk * 2 < nt) {
         uint32_t pa[4];
         pa[0] = pack2<BF>(s[2 * kk][0], s[2 * kk][1]);
         pa[1] = pack2<BF>(s[2 * kk][2], s[2 * kk][3]);
@@ -398,7 +415,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t vb[4];
-          ldsm_x4_t(vb, tile_addr(v_base, kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 16 + (lane >> 4) * 8));
+          ldsm_x4_t(vb, v_lane + kk * 2048 + xa[dp]);
           mma16816<BF>(o[2 * dp], pa, vb[0], vb[1]);
           mma16816<BF>(o[2 * dp + 1], pa, vb[2], vb[3]);
         }
@@ -494,8 +511,8 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
         const float mk0 = sMask[kb * 16 + n * 8 + 2 * t], mk1 = sMask[kb * 16 + n * 8 + 2 * t + 1];
-        d0 += exp2f(s[n][0] * sl2 + mk0 - ls0) * dp[n][0] + exp2f(s[n][1] * sl2 + mk1 - ls0) * dp[n][1];
-        d1 += exp2f(s[n][2] * sl2 + mk0 - ls1) * dp[n][2] + exp2f(s[n][3] * sl2 + mk1 - ls1) * dp[n][3];
+        d0 += ex2(s[n][0] * sl2 + mk0 - ls0) * dp[n][0] + ex2(s[n][1] * sl2 + mk1 - ls0) * dp[n][1];
+        d1 += ex2(s[n][2] * sl2 + mk0 - ls1) * dp[n][2] + ex2(s[n][3] * sl2 + mk1 - ls1) * dp[n][3];
       }
     }
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
@@ -540,10 +557,10 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
         const float mk0 = sMask[kb * 16 + n * 8 + 2 * t], mk1 = sMask[kb * 16 + n * 8 + 2 * t + 1];
-        ds[n][0] = exp2f(s[n][0] * sl2 + mk0 - ls0) * (dp[n][0] - D0) * p.scale;
-        ds[n][1] = exp2f(s[n][1] * sl2 + mk1 - ls0) * (dp[n][1] - D0) * p.scale;
-        ds[n][2] = exp2f(s[n][2] * sl2 + mk0 - ls1) * (dp[n][2] - D1) * p.scale;
-        ds[n][3] = exp2f(s[n][3] * sl2 + mk1 - ls1) * (dp[n][3] - D1) * p.scale;
+        ds[n][0] = ex2(s[n][0] * sl2 + mk0 - ls0) * (dp[n][0] - D0) * p.scale;
+        ds[n][1] = ex2(s[n][1] * sl2 + mk1 - ls0) * (dp[n][1] - D0) * p.scale;
+        ds[n][2] = ex2(s[n][2] * sl2 + mk0 - ls1) * (dp[n][2] - D1) * p.scale;
+        ds[n][3] = ex2(s[n][3] * sl2 + mk1 - ls1) * (dp[n][3] - D1) * p.scale;
       }
       uint32_t da[4] = {pack2<BF>(ds[0][0], ds[0][1]), pack2<BF>(ds[0][2], ds[0][3]), pack2<BF>(ds[1][0], ds[1][1]),
                         pack2<BF>(ds[1][2], ds[1][3])};
@@ -610,10 +627,10 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
         const int qc = qb * 16 + n * 8 + 2 * t;  // query index = fragment column
         const float l0 = sLse[qc], l1 = sLse[qc + 1], D0 = sD[qc], D1 = sD[qc + 1];
         const bool v0 = qc < p.S, v1 = qc + 1 < p.S;  // padded query rows contribute nothing
-        pt[n][0] = v0 ? exp2f(st[n][0] * sl2 + mk0 - l0) : 0.f;
-        pt[n][1] = v1 ? exp2f(st[n][1] * sl2 + mk0 - l1) : 0.f;
-        pt[n][2] = v0 ? exp2f(st[n][2] * sl2 + mk1 - l0) : 0.f;
-        pt[n][3] = v1 ? exp2f(st[n][3] * sl2 + mk1 - l1) : 0.f;
+        pt[n][0] = v0 ? ex2(st[n][0] * sl2 + mk0 - l0) : 0.f;
+        pt[n][1] = v1 ? ex2(st[n][1] * sl2 + mk0 - l1) : 0.f;
+        pt[n][2] = v0 ? ex2(st[n][2] * sl2 + mk1 - l0) : 0.f;
+        pt[n][3] = v1 ? ex2(st[n][3] * sl2 + mk1 - l1) : 0.f;
         dst_[n][0] = pt[n][0] * (dpt[n][0] - D0) * p.scale;
         dst_[n][1] = pt[n][1] * (dpt[n][1] - D1) * p.scale;
         dst_[n][2] = pt[n][2] * (dpt[n][2] - D0) * p.scale;
@@ -758,17 +775,24 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
   const size_t smem = static_cast<size_t>(S_pad) * 128 * 3 + S_pad * sizeof(float);
   dim3 grid(heads, nseq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define LAUNCH_FWD(BF, NT)                                                   \
+#define LAUNCH_FWD(BF, NT, EX)                                               \
   do {                                                                       \
-    rc = set_smem(sattn_fwd_kernel<BF, NT>, smem);                           \
+    rc = set_smem(sattn_fwd_kernel<BF, NT, EX>, smem);                       \
     if (rc) return rc;                                                       \
-    sattn_fwd_kernel<BF, NT><<<grid, 128, smem, st>>>(p);                    \
+    sattn_fwd_kernel<BF, NT, EX><<<grid, 128, smem, st>>>(p);                \
   } while (0)
-  if (fmt == 1) {
-    if (S_pad <= 64) LAUNCH_FWD(true, 8); else if (S_pad <= 128) LAUNCH_FWD(true, 16); else LAUNCH_FWD(true, 32);
-  } else {
-    if (S_pad <= 64) LAUNCH_FWD(false, 8); else if (S_pad <= 128) LAUNCH_FWD(false, 16); else LAUNCH_FWD(false, 32);
-  }
+#define LAUNCH_FWD_T(BF)                                                                              \
+  do {                                                                                                \
+    const int ntiles = S_pad >> 3;                                                                    \
+    if (ntiles == 26) LAUNCH_FWD(BF, 26, true);        /* 1 + 196 patches (224^2)            */       \
+    else if (ntiles == 30) LAUNCH_FWD(BF, 30, true);   /* fusion: 40 text + 197 video tokens */       \
+    else if (ntiles == 6) LAUNCH_FWD(BF, 6, true);     /* text, L = 40                       */       \
+    else if (ntiles <= 8) LAUNCH_FWD(BF, 8, false);                                                   \
+    else if (ntiles <= 16) LAUNCH_FWD(BF, 16, false);                                                 \
+    else LAUNCH_FWD(BF, 32, false);                                                                   \
+  } while (0)
+  if (fmt == 1) LAUNCH_FWD_T(true); else LAUNCH_FWD_T(false);
+#undef LAUNCH_FWD_T
 #undef LAUNCH_FWD
   ALPRO_CHECK_LAUNCH("alpro_seq_attn_fwd");
   return 0;

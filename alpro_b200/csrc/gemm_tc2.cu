@@ -173,32 +173,35 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int crow = lane >> 3;  // 0..3
     const int cch = lane & 7;    // float4 index within the 32-column chunk
     const float alpha = p.alpha;
+    // Pull this warp's slice of the residual / saved-derivative tile of work item `pw` towards L2 one tile ahead of
+    // its use, so that the epilogue's global loads are L2 hits instead of exposed DRAM latency.
+    auto prefetch_tile = [&](int pw) {
+      if (pw >= num_work) return;
+      const int ptile = pw / p.split_k;
+      const int pm = ptile / p.num_n_tiles;
+      const int pn = ptile - pm * p.num_n_tiles;
+      const long long prow = static_cast<long long>(pm) * (2 * BM) + cta_rank * BM + q * 32 + lane;
+      const int pcol = pn * BN + half * (BN / 2);
+      if (prow >= p.M) return;
+      if (MODE == E_GELU_GRAD || (MODE == E_GENERIC && p.aux16)) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (pcol + j * 64 < p.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux16 + prow * p.ldaux + pcol + j * 64));
+      }
+      if (MODE == E_RESID_OUT32 || (MODE == E_GENERIC && p.resid)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (pcol + j * 32 < p.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + prow * p.ldresid + pcol + j * 32));
+      }
+    };
+    prefetch_tile(cluster_id);
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const int tile = w / p.split_k;
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile - m_blk * p.num_n_tiles;
-      if (MODE == E_GELU_GRAD) {   // same idea for the saved activation derivative (16-bit, 256 B per row-half)
-        const long long prow = static_cast<long long>(m_blk) * (2 * BM) + cta_rank * BM + q * 32 + lane;
-        const int pcol = n_blk * BN + half * (BN / 2);
-        if (prow < p.M) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            if (pcol + j * 64 < p.N)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux16 + prow * p.ldaux + pcol + j * 64));
-        }
-      }
-      if (MODE == E_RESID_OUT32 || (MODE == E_GENERIC && p.resid)) {
-        // While the MMAs of this tile are still running, pull this warp's residual rows towards L2 so that the
-        // epilogue's fp32 residual loads are not exposed DRAM latency.
-        const long long prow = static_cast<long long>(m_blk) * (2 * BM) + cta_rank * BM + q * 32 + lane;
-        const int pcol = n_blk * BN + half * (BN / 2);
-        if (prow < p.M) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (pcol + j * 32 < p.N)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + prow * p.ldresid + pcol + j * 32));
-        }
-      }
+      prefetch_tile(w + num_clusters);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const long long row0 = static_cast<long long>(m_blk) * (2 * BM) + cta_rank * BM + q * 32;
