@@ -85,16 +85,27 @@ __device__ __forceinline__ float part_sum(float v) {
   return v;
 }
 
-// scores + softmax for this lane's query row i (identical in all PARTS lanes of the row)
+// Stage T rows x 64 dims of one 16-bit matrix into fp32 shared memory (coalesced 128-byte row reads).
+template <int T>
+__device__ __forceinline__ void tattn_stage(const uint16_t* src, long long ld, int fmt, int lane, float (*dst)[DH]) {
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(src + t * ld + lane * 2);
+    dst[t][lane * 2] = f16_to_32(static_cast<uint16_t>(w & 0xffff), fmt);
+    dst[t][lane * 2 + 1] = f16_to_32(static_cast<uint16_t>(w >> 16), fmt);
+  }
+}
+
+// softmax row of query i against all T keys: partial dots over this lane's DPP dims + log2(PARTS) shuffles per key
 template <int T, int DPP, int PARTS>
-__device__ __forceinline__ void tattn_row_probs(const float (&q)[DPP], const float (&k)[T][DPP], float scale,
+__device__ __forceinline__ void tattn_row_probs(const float (&q)[DPP], const float (*sk)[DH], int part, float scale,
                                                 float (&pr)[T]) {
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < T; ++j) {
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < DPP; ++e) s += q[e] * k[j][e];
+    for (int e = 0; e < DPP; ++e) s += q[e] * sk[j][part * DPP + e];
     pr[j] = part_sum<PARTS>(s) * scale;
     mx = fmaxf(mx, pr[j]);
   }
@@ -109,12 +120,13 @@ __device__ __forceinline__ void tattn_row_probs(const float (&q)[DPP], const flo
   for (int j = 0; j < T; ++j) pr[j] *= inv;
 }
 
-// grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by the n==0 warps.
+// grid: ceil(B*N*heads / 4); each warp = one (b, n, head); q/k/v live in fp32 shared memory (8 KB per warp at T=8).
 template <int T>
-__global__ void __launch_bounds__(128, 4) tattn_fwd_kernel(const TAttnParams p) {
-  constexpr int PARTS = 32 / T, DPP = DH / PARTS;
-  const int lane = threadIdx.x & 31;
-  const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(128, 6) tattn_fwd_kernel(const TAttnParams p) {
+  constexpr int PARTS = 32 / T, DPP = DH / PARTS, WPB = 4;
+  __shared__ float sQ[WPB][T][DH], sK[WPB][T][DH], sV[WPB][T][DH];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long unit = static_cast<long long>(blockIdx.x) * WPB + wib;
   const long long total = static_cast<long long>(p.B) * p.N * p.heads;
   if (unit >= total) return;
   const int head = static_cast<int>(unit % p.heads);
@@ -124,34 +136,32 @@ __global__ void __launch_bounds__(128, 4) tattn_fwd_kernel(const TAttnParams p) 
   const long long clip_rows = 1 + static_cast<long long>(p.N) * T;
   const long long row0 = b * clip_rows + 1 + static_cast<long long>(n) * T;
   if (n == 0) *reinterpret_cast<uint32_t*>(p.out + b * clip_rows * p.ld_out + head * DH + lane * 2) = 0u;  // cls row
+  const uint16_t* base = p.qkv + row0 * p.ld_qkv + head * DH;
+  tattn_stage<T>(base, p.ld_qkv, p.fmt, lane, sQ[wib]);
+  tattn_stage<T>(base + p.d, p.ld_qkv, p.fmt, lane, sK[wib]);
+  tattn_stage<T>(base + 2 * p.d, p.ld_qkv, p.fmt, lane, sV[wib]);
+  __syncwarp();
   const int i = lane / PARTS, part = lane % PARTS;
-  const int coff = head * DH + part * DPP;
-  float q[DPP], k[T][DPP], v[T][DPP], pr[T];
-  ld16<DPP>(p.qkv + (row0 + i) * p.ld_qkv + coff, q, p.fmt);
+  float q[DPP], pr[T];
 #pragma unroll
-  for (int j = 0; j < T; ++j) {
-    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, k[j], p.fmt);
-    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + 2 * p.d + coff, v[j], p.fmt);
-  }
-  tattn_row_probs<T, DPP, PARTS>(q, k, p.scale, pr);
+  for (int e = 0; e < DPP; ++e) q[e] = sQ[wib][i][part * DPP + e];
+  tattn_row_probs<T, DPP, PARTS>(q, sK[wib], part, p.scale, pr);
   float o[DPP];
 #pragma unroll
-  for (int e = 0; e < DPP; ++e) {
-    float a = 0.f;
+  for (int e = 0; e < DPP; ++e) o[e] = 0.f;
 #pragma unroll
-    for (int j = 0; j < T; ++j) a += pr[j] * v[j][e];
-    o[e] = a;
-  }
-  st16<DPP>(p.out + (row0 + i) * p.ld_out + coff, o, p.fmt);
+  for (int j = 0; j < T; ++j)
+#pragma unroll
+    for (int e = 0; e < DPP; ++e) o[e] += pr[j] * sV[wib][j][part * DPP + e];
+  st16<DPP>(p.out + (row0 + i) * p.ld_out + head * DH + part * DPP, o, p.fmt);
 }
 
 template <int T>
 __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) {
-  constexpr int PARTS = 32 / T, DPP = DH / PARTS;
-  constexpr int WPB = 4;
-  __shared__ float sQ[WPB][T][DH], sG[WPB][T][DH], sP[WPB][T][T], sDS[WPB][T][T];
+  constexpr int PARTS = 32 / T, DPP = DH / PARTS, WPB = 4;
+  __shared__ float sQ[WPB][T][DH], sK[WPB][T][DH], sV[WPB][T][DH], sG[WPB][T][DH], sP[WPB][T][T], sDS[WPB][T][T];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + wib;
+  const long long unit = static_cast<long long>(blockIdx.x) * WPB + wib;
   const long long total = static_cast<long long>(p.B) * p.N * p.heads;
   if (unit >= total) return;
   const int head = static_cast<int>(unit % p.heads);
@@ -166,39 +176,26 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
     *reinterpret_cast<uint32_t*>(z + p.d) = 0u;
     *reinterpret_cast<uint32_t*>(z + 2 * p.d) = 0u;
   }
+  const uint16_t* base = p.qkv + row0 * p.ld_qkv + head * DH;
+  tattn_stage<T>(base, p.ld_qkv, p.fmt, lane, sQ[wib]);
+  tattn_stage<T>(base + p.d, p.ld_qkv, p.fmt, lane, sK[wib]);
+  tattn_stage<T>(base + 2 * p.d, p.ld_qkv, p.fmt, lane, sV[wib]);
+  tattn_stage<T>(p.dout + row0 * p.ld_dout + head * DH, p.ld_dout, p.fmt, lane, sG[wib]);
+  __syncwarp();
   const int i = lane / PARTS, part = lane % PARTS;
-  const int coff = head * DH + part * DPP;
-  // k_j / v_j slices are streamed (re-read from L1) instead of being held: 2*T*DPP floats would not fit the register file
   float q[DPP], go[DPP], pr[T];
-  ld16<DPP>(p.qkv + (row0 + i) * p.ld_qkv + coff, q, p.fmt);
-  ld16<DPP>(p.dout + (row0 + i) * p.ld_dout + coff, go, p.fmt);
-  float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < T; ++j) {
-    float kj[DPP];
-    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, kj, p.fmt);
-    float sdot = 0.f;
-#pragma unroll
-    for (int e = 0; e < DPP; ++e) sdot += q[e] * kj[e];
-    pr[j] = part_sum<PARTS>(sdot) * p.scale;
-    mx = fmaxf(mx, pr[j]);
+  for (int e = 0; e < DPP; ++e) {
+    q[e] = sQ[wib][i][part * DPP + e];
+    go[e] = sG[wib][i][part * DPP + e];
   }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < T; ++j) {
-    pr[j] = __expf(pr[j] - mx);
-    sum += pr[j];
-  }
-  const float invs = 1.f / sum;
+  tattn_row_probs<T, DPP, PARTS>(q, sK[wib], part, p.scale, pr);
   float dp[T], dot = 0.f;
 #pragma unroll
   for (int j = 0; j < T; ++j) {
-    pr[j] *= invs;
-    float vj[DPP];
-    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + 2 * p.d + coff, vj, p.fmt);
     float sdot = 0.f;
 #pragma unroll
-    for (int e = 0; e < DPP; ++e) sdot += go[e] * vj[e];
+    for (int e = 0; e < DPP; ++e) sdot += go[e] * sV[wib][j][part * DPP + e];
     dp[j] = part_sum<PARTS>(sdot);
     dot += dp[j] * pr[j];
   }
@@ -212,17 +209,10 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
       sP[wib][i][j] = pr[j];
       sDS[wib][i][j] = ds;
     }
-    float kj[DPP];
-    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, kj, p.fmt);
 #pragma unroll
-    for (int e = 0; e < DPP; ++e) dq[e] += ds * kj[e];
+    for (int e = 0; e < DPP; ++e) dq[e] += ds * sK[wib][j][part * DPP + e];
   }
-#pragma unroll
-  for (int e = 0; e < DPP; ++e) {
-    sQ[wib][i][part * DPP + e] = q[e];
-    sG[wib][i][part * DPP + e] = go[e];
-  }
-  uint16_t* o = p.out + (row0 + i) * p.ld_out + coff;
+  uint16_t* o = p.out + (row0 + i) * p.ld_out + head * DH + part * DPP;
   st16<DPP>(o, dq, p.fmt);
   __syncwarp();
   // role switch: this lane now owns key/value row j = i
@@ -252,6 +242,8 @@ struct SAttnParams {
   // backward
   const uint16_t* dout;  // [rows, ld_o] upstream grad; with seq_div > 1 token 0 is the group's shared cls row whose
                          // forward value was the mean over the seq_div frames, so each frame receives dout / seq_div
+  const uint16_t* o_fwd;   // forward output rows [rows, ld_o] (for D = rowsum(dO * O))
+  const uint16_t* cls_fwd; // forward per-sequence token-0 outputs [nseq, d] when seq_div > 1
   uint16_t* dqkv;        // [rows, ld_qkv]
   float* dcls_qkv;       // [nseq, 3*d] fp32: per-sequence gradient of the shared cls q/k/v row (when seq_div > 1)
   long long ld_qkv, ld_o;
@@ -484,43 +476,20 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
   const float sl2 = p.scale * LOG2E;
   const int nkb = S_pad >> 4;  // 16-wide blocks along either sequence axis
 
-  // ---------------- pass 0: D_i = sum_j P_ij * dP_ij (per query row), warp per query tile
-  for (int qt = warp; qt < nkb; qt += 4) {
-    uint32_t qa[4][4], ga[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int row = qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(qa[ks], tile_addr(q_base, row, col));
-      ldsm_x4(ga[ks], tile_addr(g_base, row, col));
+  // ---------------- D_i = rowsum(dO_i * O_i): O from global (coalesced 128-byte rows), dO from the staged tile
+  for (int r = warp; r < S_pad; r += 4) {
+    float dsum = 0.f;
+    if (r < p.S) {
+      const uint16_t* orow = (r == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
+                                                        : p.o_fwd + srow(p, seq, r) * p.ld_o + head * DH;
+      const uint32_t wo = *reinterpret_cast<const uint32_t*>(orow + lane * 2);
+      const int ch = lane >> 2;   // 16-byte chunk of the dO row holding columns 2*lane, 2*lane+1
+      const uint32_t wg = *reinterpret_cast<const uint32_t*>(sG + r * 128 + ((ch ^ (r & 7)) << 4) + ((lane & 3) << 2));
+      dsum = f16_to_32(static_cast<uint16_t>(wo & 0xffff), BF ? 1 : 0) * f16_to_32(static_cast<uint16_t>(wg & 0xffff), BF ? 1 : 0) +
+             f16_to_32(static_cast<uint16_t>(wo >> 16), BF ? 1 : 0) * f16_to_32(static_cast<uint16_t>(wg >> 16), BF ? 1 : 0);
     }
-    const float ls0 = sLse[qt * 16 + g], ls1 = sLse[qt * 16 + g + 8];
-    float d0 = 0.f, d1 = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
-      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t kf[4], vf[4];
-        const int row = kb * 16 + (lane & 7) + (lane >> 4) * 8, col = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(kf, tile_addr(k_base, row, col));
-        ldsm_x4(vf, tile_addr(v_base, row, col));
-        mma16816<BF>(s[0], qa[ks], kf[0], kf[1]);
-        mma16816<BF>(s[1], qa[ks], kf[2], kf[3]);
-        mma16816<BF>(dp[0], ga[ks], vf[0], vf[1]);
-        mma16816<BF>(dp[1], ga[ks], vf[2], vf[3]);
-      }
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        const float mk0 = sMask[kb * 16 + n * 8 + 2 * t], mk1 = sMask[kb * 16 + n * 8 + 2 * t + 1];
-        d0 += ex2(s[n][0] * sl2 + mk0 - ls0) * dp[n][0] + ex2(s[n][1] * sl2 + mk1 - ls0) * dp[n][1];
-        d1 += ex2(s[n][2] * sl2 + mk0 - ls1) * dp[n][2] + ex2(s[n][3] * sl2 + mk1 - ls1) * dp[n][3];
-      }
-    }
-    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    if (t == 0) {
-      sD[qt * 16 + g] = d0;
-      sD[qt * 16 + g + 8] = d1;
-    }
+    dsum = warp_sum(dsum);
+    if (lane == 0) sD[r] = dsum;
   }
   __syncthreads();
 
@@ -798,14 +767,18 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
   return 0;
 }
 
-extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* dout,
-                                  int64_t ld_o, void* dqkv, float* dcls_qkv_scratch, int S, int nseq,
+extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* o_fwd,
+                                  const void* cls_fwd, const void* dout, int64_t ld_o, void* dqkv,
+                                  float* dcls_qkv_scratch, int S, int nseq,
                                   int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
                                   void* stream) {
   SAttnParams p{};
   int rc = fill_sattn(p, qkv, ld_qkv, mask, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale);
   if (rc) return rc;
-  ALPRO_REQUIRE(lse && dout && dqkv && (ld_o % 8) == 0, "alpro_seq_attn_bwd: bad args");
+  ALPRO_REQUIRE(lse && dout && dqkv && o_fwd && (ld_o % 8) == 0, "alpro_seq_attn_bwd: bad args");
+  ALPRO_REQUIRE(seq_div == 1 || cls_fwd, "alpro_seq_attn_bwd: shared-cls layout needs the per-sequence cls outputs");
+  p.o_fwd = static_cast<const uint16_t*>(o_fwd);
+  p.cls_fwd = static_cast<const uint16_t*>(cls_fwd);
   ALPRO_REQUIRE(seq_div == 1 || dcls_qkv_scratch, "alpro_seq_attn_bwd: shared-cls layout needs the fp32 scratch");
   p.lse = const_cast<float*>(lse); p.dout = static_cast<const uint16_t*>(dout); p.ld_o = ld_o;
   p.dqkv = static_cast<uint16_t*>(dqkv);

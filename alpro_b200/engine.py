@@ -221,7 +221,8 @@ class VisualEncoder:
             ops.gemm16(hdn, w("mlp.fc2.weight"), bias=g("mlp.fc2.bias"), resid=x2, out32=x3)
             if save:
                 ctx["blocks"].append(dict(x=x, a_t=a_t, st_t=st_t, qkv_t=qkv_t, o_t=o_t, p_t=p_t, x1=x1, a_s=a_s,
-                                          st_s=st_s, qkv_s=qkv_s, o_s=o_s, lse=lse, x2=x2, a_m=a_m, st_m=st_m, hdn=hdn,
+                                          st_s=st_s, qkv_s=qkv_s, o_s=o_s, cls_o=cls_o, lse=lse, x2=x2, a_m=a_m, st_m=st_m,
+                                          hdn=hdn,
                                           pre=pre))
             x = x3
         xn = _empty((M, d), torch.float32, dev)
@@ -283,7 +284,8 @@ class VisualEncoder:
             # ---- spatial attention
             ops.gemm16(dx16, w("attn.proj.weight"), b_layout=MNMAJOR, out16=da)          # d o_s
             wgrad(dx16, c["o_s"], b + "attn.proj.weight")
-            ops.seq_attn_bwd(c["qkv_s"], None, c["lse"], da, d3, scratch, 1 + N, B * T, heads, T, T, Sc, scale)
+            ops.seq_attn_bwd(c["qkv_s"], None, c["lse"], c["o_s"], c["cls_o"], da, d3, scratch, 1 + N, B * T, heads, T, T,
+                             Sc, scale)
             ops.gemm16(d3, w("attn.qkv.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d3, c["a_s"], b + "attn.qkv.weight", b + "attn.qkv.bias")
             # dx16 <- grad wrt x1 with cls rows zeroed (the temporal branch never touches cls rows)
@@ -451,7 +453,8 @@ class BertEncoder:
             ops.gemm16(dz1_16, w("attention.output.dense.weight"), b_layout=MNMAJOR, out16=dcx)
             wgrad(dz1_16, c["cx"], G[l + "attention.output.dense.weight"])
             dqkv = _empty((M, 3 * h), dt, dev)
-            ops.seq_attn_bwd(c["qkv"], ctx["mask"], c["lse"], dcx, dqkv, None, S_len, nseq, heads, 1, 1, S_len, scale)
+            ops.seq_attn_bwd(c["qkv"], ctx["mask"], c["lse"], c["cx"], None, dcx, dqkv, None, S_len, nseq, heads, 1, 1,
+                             S_len, scale)
             Wq, _ = self._qkv(P, W, l)
             dx32 = da32  # reuse
             ops.gemm16(dqkv, Wq, b_layout=MNMAJOR, resid=dz1, out32=dx32)

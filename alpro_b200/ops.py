@@ -209,8 +209,10 @@ def seq_attn_fwd(qkv, mask, o, cls_o, lse, S, nseq, heads, seq_div, stride, clip
                                 heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()), "alpro_seq_attn_fwd")
 
 
-def seq_attn_bwd(qkv, mask, lse, dout, dqkv, scratch, S, nseq, heads, seq_div, stride, clip_rows, scale):
-    check(_L.alpro_seq_attn_bwd(_p(qkv), qkv.stride(0), _p(mask), _p(lse), _p(dout), dout.stride(0), _p(dqkv),
+def seq_attn_bwd(qkv, mask, lse, o_fwd, cls_fwd, dout, dqkv, scratch, S, nseq, heads, seq_div, stride, clip_rows, scale):
+    assert o_fwd.stride(0) == dout.stride(0)
+    check(_L.alpro_seq_attn_bwd(_p(qkv), qkv.stride(0), _p(mask), _p(lse), _p(o_fwd), _p(cls_fwd), _p(dout),
+                                dout.stride(0), _p(dqkv),
                                 _p(scratch), S, nseq, heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()),
           "alpro_seq_attn_bwd")
 

@@ -142,9 +142,10 @@ int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const void* dout, i
 int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* mask, void* o, int64_t ld_o, void* cls_o, float* lse,
                        int S, int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
                        void* stream);
-int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* dout,
-                       int64_t ld_o, void* dqkv, float* dcls_qkv_scratch, int S, int nseq, int heads, int fmt, int seq_div,
-                       int stride, int64_t clip_rows, float scale, void* stream);
+/* backward: o_fwd = the forward output rows, cls_fwd = the forward per-sequence token-0 outputs (cls_o, seq_div > 1 only) */
+int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* o_fwd,
+                       const void* cls_fwd, const void* dout, int64_t ld_o, void* dqkv, float* dcls_qkv_scratch, int S,
+                       int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Task-head kernels, fp32 (alpro_b200/csrc/heads.cu)

@@ -300,7 +300,7 @@ def test_seq_attention_bert_layout(S, dt):
     assert rel(o.float(), refo.detach()) < tol
     do = torch.randn(nseq * S, d, device=DEV, generator=gen).to(dt)
     dqkv = torch.empty(nseq * S, 3 * d, device=DEV, dtype=dt)
-    ops.seq_attn_bwd(qkv, mask, lse, do, dqkv, None, S, nseq, heads, 1, 1, S, scale)
+    ops.seq_attn_bwd(qkv, mask, lse, o, None, do, dqkv, None, S, nseq, heads, 1, 1, S, scale)
     ref.backward(do.float().view(nseq, S, heads, 64).permute(0, 2, 1, 3))
     want = x.grad.permute(1, 3, 0, 2, 4).reshape(nseq * S, 3 * d)
     assert rel(dqkv.float(), want) < (4e-3 if dt == torch.float16 else 3e-2)
@@ -332,7 +332,7 @@ def test_seq_attention_vit_layout(N, T):
     do = torch.randn(B * Sc, d, device=DEV, generator=gen).half()
     dqkv = torch.empty(B * Sc, 3 * d, device=DEV, dtype=torch.float16)
     scratch = torch.empty(B * T, 3 * d, device=DEV)
-    ops.seq_attn_bwd(qkv, None, lse, do, dqkv, scratch, S, B * T, heads, T, T, Sc, 0.125)
+    ops.seq_attn_bwd(qkv, None, lse, o, cls_o, do, dqkv, scratch, S, B * T, heads, T, T, Sc, 0.125)
     want.backward(do.float().view(B, Sc, d))
     assert rel(dqkv.float().view(B, Sc, 3 * d), x.grad) < 4e-3
 
