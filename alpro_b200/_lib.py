@@ -26,6 +26,7 @@ class GemmEpilogue(ctypes.Structure):
         ("out16_fmt", ctypes.c_int32), ("out16b_fmt", ctypes.c_int32), ("aux_fmt", ctypes.c_int32),
         ("act", ctypes.c_int32), ("skip_period", ctypes.c_int32), ("split_k", ctypes.c_int32),
         ("alpha", c_float),
+        ("row_scale_acc", c_void_p), ("row_scale_bias", c_void_p),
     ]
 
 
@@ -61,6 +62,8 @@ def parse_header(path=HEADER_PATH):
                     argtypes.append(c_void_p)
                 elif re.match(r"(const )?int64_t\b", a):
                     argtypes.append(c_int64)
+                elif re.match(r"(const )?uint32_t\b", a):
+                    argtypes.append(ctypes.c_uint32)
                 elif re.match(r"(const )?(int|int32_t)\b", a):
                     argtypes.append(c_int)
                 elif re.match(r"(const )?float\b", a):

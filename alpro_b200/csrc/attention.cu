@@ -120,13 +120,36 @@ __device__ __forceinline__ void tattn_row_probs(const float (&q)[DPP], const flo
   for (int j = 0; j < T; ++j) pr[j] *= inv;
 }
 
-// grid: ceil(B*N*heads / 4); each warp = one (b, n, head); q/k/v live in fp32 shared memory (8 KB per warp at T=8).
+// scores + softmax for this lane's query row i (identical in all PARTS lanes of the row)
+template <int T, int DPP, int PARTS>
+__device__ __forceinline__ void tattn_row_probs_reg(const float (&q)[DPP], const float (&k)[T][DPP], float scale,
+                                                float (&pr)[T]) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < DPP; ++e) s += q[e] * k[j][e];
+    pr[j] = part_sum<PARTS>(s) * scale;
+    mx = fmaxf(mx, pr[j]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    pr[j] = __expf(pr[j] - mx);
+    sum += pr[j];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int j = 0; j < T; ++j) pr[j] *= inv;
+}
+
+// grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by the n==0 warps.
 template <int T>
-__global__ void __launch_bounds__(128, 6) tattn_fwd_kernel(const TAttnParams p) {
-  constexpr int PARTS = 32 / T, DPP = DH / PARTS, WPB = 4;
-  __shared__ float sQ[WPB][T][DH], sK[WPB][T][DH], sV[WPB][T][DH];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long unit = static_cast<long long>(blockIdx.x) * WPB + wib;
+__global__ void __launch_bounds__(128, 3) tattn_fwd_kernel(const TAttnParams p) {
+  constexpr int PARTS = 32 / T, DPP = DH / PARTS;
+  const int lane = threadIdx.x & 31;
+  const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = static_cast<long long>(p.B) * p.N * p.heads;
   if (unit >= total) return;
   const int head = static_cast<int>(unit % p.heads);
@@ -136,24 +159,25 @@ __global__ void __launch_bounds__(128, 6) tattn_fwd_kernel(const TAttnParams p) 
   const long long clip_rows = 1 + static_cast<long long>(p.N) * T;
   const long long row0 = b * clip_rows + 1 + static_cast<long long>(n) * T;
   if (n == 0) *reinterpret_cast<uint32_t*>(p.out + b * clip_rows * p.ld_out + head * DH + lane * 2) = 0u;  // cls row
-  const uint16_t* base = p.qkv + row0 * p.ld_qkv + head * DH;
-  tattn_stage<T>(base, p.ld_qkv, p.fmt, lane, sQ[wib]);
-  tattn_stage<T>(base + p.d, p.ld_qkv, p.fmt, lane, sK[wib]);
-  tattn_stage<T>(base + 2 * p.d, p.ld_qkv, p.fmt, lane, sV[wib]);
-  __syncwarp();
   const int i = lane / PARTS, part = lane % PARTS;
-  float q[DPP], pr[T];
+  const int coff = head * DH + part * DPP;
+  float q[DPP], k[T][DPP], v[T][DPP], pr[T];
+  ld16<DPP>(p.qkv + (row0 + i) * p.ld_qkv + coff, q, p.fmt);
 #pragma unroll
-  for (int e = 0; e < DPP; ++e) q[e] = sQ[wib][i][part * DPP + e];
-  tattn_row_probs<T, DPP, PARTS>(q, sK[wib], part, p.scale, pr);
+  for (int j = 0; j < T; ++j) {
+    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, k[j], p.fmt);
+    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + 2 * p.d + coff, v[j], p.fmt);
+  }
+  tattn_row_probs_reg<T, DPP, PARTS>(q, k, p.scale, pr);
   float o[DPP];
 #pragma unroll
-  for (int e = 0; e < DPP; ++e) o[e] = 0.f;
+  for (int e = 0; e < DPP; ++e) {
+    float a = 0.f;
 #pragma unroll
-  for (int j = 0; j < T; ++j)
-#pragma unroll
-    for (int e = 0; e < DPP; ++e) o[e] += pr[j] * sV[wib][j][part * DPP + e];
-  st16<DPP>(p.out + (row0 + i) * p.ld_out + head * DH + part * DPP, o, p.fmt);
+    for (int j = 0; j < T; ++j) a += pr[j] * v[j][e];
+    o[e] = a;
+  }
+  st16<DPP>(p.out + (row0 + i) * p.ld_out + coff, o, p.fmt);
 }
 
 template <int T>
@@ -244,6 +268,7 @@ struct SAttnParams {
                          // forward value was the mean over the seq_div frames, so each frame receives dout / seq_div
   const uint16_t* o_fwd;   // forward output rows [rows, ld_o] (for D = rowsum(dO * O))
   const uint16_t* cls_fwd; // forward per-sequence token-0 outputs [nseq, d] when seq_div > 1
+  const float* cls_weight; // optional [nseq]: d(group cls row)/d(frame cls output); default 1/seq_div (plain mean)
   uint16_t* dqkv;        // [rows, ld_qkv]
   float* dcls_qkv;       // [nseq, 3*d] fp32: per-sequence gradient of the shared cls q/k/v row (when seq_div > 1)
   long long ld_qkv, ld_o;
@@ -452,7 +477,7 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
   load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, seq, S_pad, sK, nullptr);
   load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S_pad, sV, nullptr);
   load_tile(p, p.dout, p.ld_o, head * DH, seq, S_pad, sG, nullptr);
-  const float gscale0 = 1.f / p.seq_div;  // d(mean_t cls_t) / d cls_t
+  const float gscale0 = p.cls_weight ? p.cls_weight[seq] : 1.f / p.seq_div;  // d(weighted mean_t cls_t) / d cls_t
   for (int j = threadIdx.x; j < S_pad; j += blockDim.x) {
     sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
     sLse[j] = j < p.S ? p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + j] : 0.f;
@@ -476,20 +501,32 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
   const float sl2 = p.scale * LOG2E;
   const int nkb = S_pad >> 4;  // 16-wide blocks along either sequence axis
 
-  // ---------------- D_i = rowsum(dO_i * O_i): O from global (coalesced 128-byte rows), dO from the staged tile
-  for (int r = warp; r < S_pad; r += 4) {
-    float dsum = 0.f;
-    if (r < p.S) {
-      const uint16_t* orow = (r == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
-                                                        : p.o_fwd + srow(p, seq, r) * p.ld_o + head * DH;
-      const uint32_t wo = *reinterpret_cast<const uint32_t*>(orow + lane * 2);
-      const int ch = lane >> 2;   // 16-byte chunk of the dO row holding columns 2*lane, 2*lane+1
-      const uint32_t wg = *reinterpret_cast<const uint32_t*>(sG + r * 128 + ((ch ^ (r & 7)) << 4) + ((lane & 3) << 2));
-      dsum = f16_to_32(static_cast<uint16_t>(wo & 0xffff), BF ? 1 : 0) * f16_to_32(static_cast<uint16_t>(wg & 0xffff), BF ? 1 : 0) +
-             f16_to_32(static_cast<uint16_t>(wo >> 16), BF ? 1 : 0) * f16_to_32(static_cast<uint16_t>(wg >> 16), BF ? 1 : 0);
+  // ---------------- D_i = rowsum(dO_i * O_i): O from global (coalesced 128-byte rows, 8 rows in flight per warp),
+  // dO from the staged tile
+  for (int r0 = warp; r0 < S_pad; r0 += 32) {
+    uint32_t wo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 4 * u;
+      wo[u] = 0u;
+      if (r < p.S) {
+        const uint16_t* orow = (r == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
+                                                          : p.o_fwd + srow(p, seq, r) * p.ld_o + head * DH;
+        wo[u] = *reinterpret_cast<const uint32_t*>(orow + lane * 2);
+      }
     }
-    dsum = warp_sum(dsum);
-    if (lane == 0) sD[r] = dsum;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 4 * u;
+      if (r < S_pad) {   // warp-uniform
+        const int ch = lane >> 2;   // 16-byte chunk of the dO row holding columns 2*lane, 2*lane+1
+        const uint32_t wg = *reinterpret_cast<const uint32_t*>(sG + r * 128 + ((ch ^ (r & 7)) << 4) + ((lane & 3) << 2));
+        float dsum = f16_to_32(static_cast<uint16_t>(wo[u] & 0xffff), BF ? 1 : 0) * f16_to_32(static_cast<uint16_t>(wg & 0xffff), BF ? 1 : 0) +
+                     f16_to_32(static_cast<uint16_t>(wo[u] >> 16), BF ? 1 : 0) * f16_to_32(static_cast<uint16_t>(wg >> 16), BF ? 1 : 0);
+        dsum = warp_sum(dsum);
+        if (lane == 0) sD[r] = dsum;
+      }
+    }
   }
   __syncthreads();
 
@@ -768,8 +805,8 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
 }
 
 extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* o_fwd,
-                                  const void* cls_fwd, const void* dout, int64_t ld_o, void* dqkv,
-                                  float* dcls_qkv_scratch, int S, int nseq,
+                                  const void* cls_fwd, const float* cls_weight, const void* dout, int64_t ld_o,
+                                  void* dqkv, float* dcls_qkv_scratch, int S, int nseq,
                                   int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
                                   void* stream) {
   SAttnParams p{};
@@ -779,6 +816,7 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   ALPRO_REQUIRE(seq_div == 1 || cls_fwd, "alpro_seq_attn_bwd: shared-cls layout needs the per-sequence cls outputs");
   p.o_fwd = static_cast<const uint16_t*>(o_fwd);
   p.cls_fwd = static_cast<const uint16_t*>(cls_fwd);
+  p.cls_weight = cls_weight;
   ALPRO_REQUIRE(seq_div == 1 || dcls_qkv_scratch, "alpro_seq_attn_bwd: shared-cls layout needs the fp32 scratch");
   p.lse = const_cast<float*>(lse); p.dout = static_cast<const uint16_t*>(dout); p.ld_o = ld_o;
   p.dqkv = static_cast<uint16_t*>(dqkv);

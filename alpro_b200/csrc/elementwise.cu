@@ -3,6 +3,7 @@
 // All are written for coalesced 128-bit accesses with one warp per token row where a row reduction is needed.
 #include "common.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace alpro {
 namespace {
@@ -30,13 +31,28 @@ __global__ void cast_f32_to_16_kernel(const float* __restrict__ src, uint16_t* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------ dropout mask
+// out[i] = keep_i / (1 - p) with keep_i ~ Bernoulli(1 - p) from the counter hash (nn.Dropout, xbert.py:178,331,358,436)
+__global__ void dropout_mask_kernel(uint16_t* __restrict__ out, int fmt, long long n, uint32_t thr, float scale,
+                                    uint32_t seed) {
+  const long long pairs = (n + 1) >> 1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint32_t r = rand16x2(seed, static_cast<uint64_t>(i));
+    const float a = (r & 0xffff) >= thr ? scale : 0.f, b = (r >> 16) >= thr ? scale : 0.f;
+    if (2 * i + 1 < n) *reinterpret_cast<uint32_t*>(out + 2 * i) = pack2_16(a, b, fmt);
+    else out[2 * i] = f32_to_16(a, fmt);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm fwd
 // One warp per row; two-pass statistics held in registers (matches torch: var = mean((x-mean)^2), biased).
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float eps, long long M, int d,
                                      float* __restrict__ out32, long long ld32, uint16_t* __restrict__ out16,
                                      long long ld16, int fmt, float* __restrict__ mean_out,
-                                     float* __restrict__ rstd_out) {
+                                     float* __restrict__ rstd_out, const uint16_t* __restrict__ mul16,
+                                     long long ldmul) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -78,6 +94,11 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
       y.y = (v[i].y - mean) * rstd * g.y + b.y;
       y.z = (v[i].z - mean) * rstd * g.z + b.z;
       y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (mul16) {   // dropout applied to the normalised output (BertEmbeddings, xbert.py:211-212)
+        const uint2 mw = reinterpret_cast<const uint2*>(mul16 + row * ldmul)[c];
+        y.x *= f16_to_32(static_cast<uint16_t>(mw.x & 0xffff), fmt); y.y *= f16_to_32(static_cast<uint16_t>(mw.x >> 16), fmt);
+        y.z *= f16_to_32(static_cast<uint16_t>(mw.y & 0xffff), fmt); y.w *= f16_to_32(static_cast<uint16_t>(mw.y >> 16), fmt);
+      }
       if (out32) reinterpret_cast<float4*>(out32 + row * ld32)[c] = y;
       if (out16) {
         uint2 w;
@@ -100,7 +121,11 @@ __global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __res
                                      int d, float* __restrict__ dx32, long long lddx, int accumulate,
                                      uint16_t* __restrict__ dx16, long long lddx16, int fmt, int zero_period,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float param_scale,
-                                     float* __restrict__ colsum, int colsum_zero_period) {
+                                     float* __restrict__ colsum, int colsum_zero_period,
+                                     const uint16_t* __restrict__ dy_mul16, long long lddymul,
+                                     const uint16_t* __restrict__ dx16_mul16, long long lddxmul,
+                                     const float* __restrict__ dx16_row_scale,
+                                     const float* __restrict__ colsum_row_scale) {
   extern __shared__ float red[];  // [warps][d] x 2
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -132,6 +157,11 @@ __global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __res
           dv[i].y = f16_to_32(static_cast<uint16_t>(w.x >> 16), dy_kind - 1);
           dv[i].z = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), dy_kind - 1);
           dv[i].w = f16_to_32(static_cast<uint16_t>(w.y >> 16), dy_kind - 1);
+        }
+        if (dy_mul16) {   // upstream dropout on this LayerNorm's output
+          const uint2 mw = reinterpret_cast<const uint2*>(dy_mul16 + row * lddymul)[c];
+          dv[i].x *= f16_to_32(static_cast<uint16_t>(mw.x & 0xffff), fmt); dv[i].y *= f16_to_32(static_cast<uint16_t>(mw.x >> 16), fmt);
+          dv[i].z *= f16_to_32(static_cast<uint16_t>(mw.y & 0xffff), fmt); dv[i].w *= f16_to_32(static_cast<uint16_t>(mw.y >> 16), fmt);
         }
       }
     }
@@ -166,14 +196,25 @@ __global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __res
           o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
         }
         dxrow[c] = o;
-        if (cs_on) { ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w; }
+        // the 16-bit copy / bias column sums are the gradient of the *branch output* that feeds this residual sum:
+        // it carries that branch's dropout mask and stochastic-depth row scale
+        if (dx16_mul16) {
+          const uint2 mw = reinterpret_cast<const uint2*>(dx16_mul16 + row * lddxmul)[c];
+          o.x *= f16_to_32(static_cast<uint16_t>(mw.x & 0xffff), fmt); o.y *= f16_to_32(static_cast<uint16_t>(mw.x >> 16), fmt);
+          o.z *= f16_to_32(static_cast<uint16_t>(mw.y & 0xffff), fmt); o.w *= f16_to_32(static_cast<uint16_t>(mw.y >> 16), fmt);
+        }
+        if (cs_on) {
+          const float cs = colsum_row_scale ? colsum_row_scale[row] : (dx16_row_scale ? dx16_row_scale[row] : 1.f);
+          ac[i].x += o.x * cs; ac[i].y += o.y * cs; ac[i].z += o.z * cs; ac[i].w += o.w * cs;
+        }
         if (dx16) {
           uint2 w;
           if (zero16) {
             w.x = w.y = 0u;
           } else {
-            w.x = pack2_16(o.x, o.y, fmt);
-            w.y = pack2_16(o.z, o.w, fmt);
+            const float rsv = dx16_row_scale ? dx16_row_scale[row] : 1.f;
+            w.x = pack2_16(o.x * rsv, o.y * rsv, fmt);
+            w.y = pack2_16(o.z * rsv, o.w * rsv, fmt);
           }
           reinterpret_cast<uint2*>(dx16 + row * lddx16)[c] = w;
         }
@@ -510,7 +551,7 @@ __global__ void fusion_gather_bwd_kernel(const float* __restrict__ dout, const i
 // mean over t of the T per-frame cls rows -> the clip's canonical cls row (Block.forward vit.py:184-187, moved in front
 // of the linear `proj`, with which the mean commutes).
 __global__ void cls_mean_fwd_kernel(const uint16_t* __restrict__ cls_t, uint16_t* __restrict__ o, long long ldo,
-                                    int fmt, int B, int T, int S, int d) {
+                                    int fmt, int B, int T, int S, int d, const float* __restrict__ wgt) {
   // cls_t: [B, T, d]; o row b*S gets the mean
   const long long total = static_cast<long long>(B) * d;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -518,7 +559,8 @@ __global__ void cls_mean_fwd_kernel(const uint16_t* __restrict__ cls_t, uint16_t
     const int b = static_cast<int>(i / d);
     const int c = static_cast<int>(i - static_cast<long long>(b) * d);
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s += f16_to_32(cls_t[(static_cast<long long>(b) * T + t) * d + c], fmt);
+    for (int t = 0; t < T; ++t)   // wgt: per-frame stochastic-depth factor mask/keep (vit.py:181-187 in train mode)
+      s += f16_to_32(cls_t[(static_cast<long long>(b) * T + t) * d + c], fmt) * (wgt ? wgt[b * T + t] : 1.f);
     o[static_cast<long long>(b) * S * ldo + c] = f32_to_16(s / T, fmt);
   }
 }
@@ -548,13 +590,15 @@ extern "C" int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int 
 
 extern "C" int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
                                    int64_t M, int d, float* out32, int64_t ld32, void* out16, int64_t ld16,
-                                   int out16_fmt, float* mean, float* rstd, void* stream) {
+                                   int out16_fmt, float* mean, float* rstd, const void* mul16, int64_t ldmul,
+                                   void* stream) {
   ALPRO_REQUIRE(x && gamma && beta && M > 0, "alpro_layernorm_fwd: bad args");
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_fwd: d=%d unsupported (multiple of 4, <= 1024)", d);
   ALPRO_REQUIRE(ldx % 4 == 0 && (!out32 || ld32 % 4 == 0) && (!out16 || ld16 % 4 == 0), "alpro_layernorm_fwd: ld");
   const int wpb = 8;
   layernorm_fwd_kernel<<<static_cast<unsigned>(cdiv(M, wpb)), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ldx, gamma, beta, eps, M, d, out32, ld32, static_cast<uint16_t*>(out16), ld16, out16_fmt, mean, rstd);
+      x, ldx, gamma, beta, eps, M, d, out32, ld32, static_cast<uint16_t*>(out16), ld16, out16_fmt, mean, rstd,
+      static_cast<const uint16_t*>(mul16), ldmul);
   ALPRO_CHECK_LAUNCH("alpro_layernorm_fwd");
   return 0;
 }
@@ -563,7 +607,9 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
                                    const float* mean, const float* rstd, const float* gamma, int64_t M, int d,
                                    float* dx32, int64_t lddx, int accumulate, void* dx16, int64_t lddx16,
                                    int dx16_fmt, int zero_period, float* dgamma, float* dbeta, float param_scale,
-                                   float* colsum, int colsum_zero_period, void* stream) {
+                                   float* colsum, int colsum_zero_period, const void* dy_mul16, int64_t lddymul,
+                                   const void* dx16_mul16, int64_t lddxmul, const float* dx16_row_scale,
+                                   const float* colsum_row_scale, void* stream) {
   ALPRO_REQUIRE(dy && x && mean && rstd && gamma && dx32 && M > 0, "alpro_layernorm_bwd: bad args");
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_bwd: d=%d unsupported", d);
   ALPRO_REQUIRE(dy_kind >= 0 && dy_kind <= 2, "alpro_layernorm_bwd: dy_kind");
@@ -577,7 +623,9 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
   layernorm_bwd_kernel<NV><<<grid, wpb * 32, smem, st>>>(dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, \
                                                          accumulate, static_cast<uint16_t*>(dx16), lddx16, dx16_fmt,   \
                                                          zero_period, dgamma, dbeta, param_scale, colsum,              \
-                                                         colsum_zero_period)
+                                                         colsum_zero_period, static_cast<const uint16_t*>(dy_mul16),   \
+                                                         lddymul, static_cast<const uint16_t*>(dx16_mul16), lddxmul,   \
+                                                         dx16_row_scale, colsum_row_scale)
   if (d <= 256) ALPRO_LN_BWD(2);
   else if (d <= 768) ALPRO_LN_BWD(6);
   else ALPRO_LN_BWD(8);
@@ -696,10 +744,18 @@ extern "C" int alpro_fusion_gather_bwd(const float* dout, const int32_t* ti, con
 }
 
 extern "C" int alpro_cls_mean_fwd(const void* cls_t, void* o, int64_t ldo, int fmt, int B, int T, int S, int d,
-                                  void* stream) {
+                                  const float* frame_weight, void* stream) {
   ALPRO_REQUIRE(cls_t && o, "alpro_cls_mean_fwd: bad args");
   cls_mean_fwd_kernel<<<grid_for(static_cast<long long>(B) * d, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint16_t*>(cls_t), static_cast<uint16_t*>(o), ldo, fmt, B, T, S, d);
+      static_cast<const uint16_t*>(cls_t), static_cast<uint16_t*>(o), ldo, fmt, B, T, S, d, frame_weight);
   ALPRO_CHECK_LAUNCH("alpro_cls_mean_fwd");
+  return 0;
+}
+
+extern "C" int alpro_dropout_mask(void* out16, int fmt, int64_t n, float p, uint32_t seed, void* stream) {
+  ALPRO_REQUIRE(out16 && n > 0 && p >= 0.f && p < 1.f, "alpro_dropout_mask: bad args");
+  dropout_mask_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint16_t*>(out16), fmt, n, drop_threshold(p), 1.0f / (1.0f - p), seed);
+  ALPRO_CHECK_LAUNCH("alpro_dropout_mask");
   return 0;
 }

@@ -24,6 +24,8 @@ struct GemmKParams {
   int out16_fmt, out16b_fmt, aux_fmt;
   int act;
   int skip_period;
+  const float* rs_acc;   // optional per-row scale of (alpha*acc)   [M]  (drop_path: mask/keep of the row's sample)
+  const float* rs_bias;  // optional per-row scale of the bias term  [M]  (defaults to rs_acc)
   int vec_ok;  // all leading dims / pointers allow vector accesses on 4-column groups
   float alpha;
 };
@@ -123,9 +125,19 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[N
 #pragma unroll
     for (int i = 0; i < NR; ++i) load4_32(p.resid + lrow[i] * p.ldresid + col, rr[i], full, ncol);
   }
+  if (p.rs_acc) {   // stochastic depth: v = rs_acc[row] * acc + rs_bias[row] * bias
 #pragma unroll
-  for (int i = 0; i < NR; ++i) {
-    v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w;
+    for (int i = 0; i < NR; ++i) {
+      const float ra = __ldg(p.rs_acc + lrow[i]);
+      const float rb = p.rs_bias ? __ldg(p.rs_bias + lrow[i]) : ra;
+      v[i][0] = fmaf(v[i][0], ra, b4.x * rb); v[i][1] = fmaf(v[i][1], ra, b4.y * rb);
+      v[i][2] = fmaf(v[i][2], ra, b4.z * rb); v[i][3] = fmaf(v[i][3], ra, b4.w * rb);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w;
+    }
   }
   if (act == ALPRO_ACT_GELU) {
     // out16b receives gelu'(pre) (NOT the pre-activation): the backward epilogue is then a plain multiply

@@ -373,6 +373,7 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   if (ep->split_k != 0 && ep->split_k != 1) {
     ALPRO_REQUIRE(ep->out32 && !ep->out16 && !ep->out16b && !ep->bias && !ep->resid && ep->act == ALPRO_ACT_NONE,
                   "alpro_gemm16: split-K supports only out32 += alpha*acc");
+    ALPRO_REQUIRE(!ep->row_scale_acc, "alpro_gemm16: split-K does not take row scales");
   }
   p.a_mn = a_layout == ALPRO_MNMAJOR;
   p.b_mn = b_layout == ALPRO_MNMAJOR;
@@ -388,6 +389,8 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   p.act = ep->act;
   p.skip_period = ep->skip_period;
   p.alpha = ep->alpha;
+  p.rs_acc = ep->row_scale_acc;
+  p.rs_bias = ep->row_scale_bias;
   bool vec = true;
   if (p.bias) vec = vec && aligned16(p.bias);
   if (p.out32) vec = vec && aligned16(p.out32) && (p.ld32 % 4) == 0;

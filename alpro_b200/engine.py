@@ -144,8 +144,31 @@ class VisualEncoder:
             tim = tim[tim_idx].contiguous()
         return pos.contiguous(), tim.contiguous(), pos_idx, tim_idx
 
-    def forward(self, P, W, frames, save):
-        """frames fp32 [B,T,3,H,W] -> video_embeds fp32 [B, 1+N, d]; ctx holds what the backward needs."""
+    def _drop_path_scales(self, i, rate, B, N, T, dev):
+        """Per-sample stochastic-depth factors mask/keep (DropPath, vit_utils.py:137-162; rate linearly scaled over
+        depth, vit.py:272-277) expanded to token rows. The three branches use different sample granularity exactly as
+        the reference's mask shape (x.shape[0],1,1): temporal per (b,h,w), spatial per (b,t), MLP per b."""
+        p = rate * i / max(self.depth - 1, 1)
+        if p <= 0.0:
+            return None
+        keep = 1.0 - p
+        Sc = 1 + N * T
+        m_t = torch.bernoulli(torch.full((B, N), keep, device=dev)) / keep
+        m_s = torch.bernoulli(torch.full((B, T), keep, device=dev)) / keep
+        m_m = torch.bernoulli(torch.full((B,), keep, device=dev)) / keep
+        zero = torch.zeros(B, 1, device=dev)
+        one = torch.ones(B, 1, device=dev)
+        rs_t = torch.cat([zero, m_t.view(B, N, 1).expand(B, N, T).reshape(B, N * T)], 1).reshape(-1).contiguous()
+        sp = m_s.view(B, 1, T).expand(B, N, T).reshape(B, N * T)
+        rsa = torch.cat([one, sp], 1).reshape(-1).contiguous()
+        rsb = torch.cat([m_s.mean(dim=1, keepdim=True), sp], 1).reshape(-1).contiguous()
+        rs_m = m_m.view(B, 1).expand(B, Sc).reshape(-1).contiguous()
+        return dict(rs_t=rs_t, rsa=rsa, rsb=rsb, rs_m=rs_m, m_s=m_s.reshape(-1).contiguous(),
+                    cls_w=(m_s / T).reshape(-1).contiguous(), raw=dict(m_t=m_t, m_s=m_s, m_m=m_m))
+
+    def forward(self, P, W, frames, save, drop_path_rate=0.0):
+        """frames fp32 [B,T,3,H,W] -> video_embeds fp32 [B, 1+N, d]; ctx holds what the backward needs.
+        drop_path_rate > 0 enables train-mode stochastic depth."""
         B, T, C, H, Wd = frames.shape
         dev = frames.device
         d, heads, dt = self.d, self.heads, self.dtype
@@ -184,6 +207,7 @@ class VisualEncoder:
             b = f"{p}blocks.{i}."
             g = lambda n: P[b + n].detach()
             w = lambda n: W.get(b + n, P[b + n])
+            dp = self._drop_path_scales(i, drop_path_rate, B, N, T, dev) if drop_path_rate > 0 else None
             # ---- temporal attention branch (vit.py:146-162)
             a_t = buf("a_t", (M, d), dt)
             st_t = buf("st_t", (2, M), torch.float32)
@@ -194,7 +218,8 @@ class VisualEncoder:
             o_t = buf("o_t", (M, d), dt)
             ops.temporal_attn_fwd(qkv_t, o_t, B, N, T, heads, scale)
             p_t = buf("p_t", (M, d), dt)
-            ops.gemm16(o_t, w("temporal_attn.proj.weight"), bias=g("temporal_attn.proj.bias"), out16=p_t)
+            ops.gemm16(o_t, w("temporal_attn.proj.weight"), bias=g("temporal_attn.proj.bias"), out16=p_t,
+                       row_scale=dp["rs_t"] if dp else None)
             x1 = buf("x1", (M, d), torch.float32)
             ops.gemm16(p_t, w("temporal_fc.weight"), bias=g("temporal_fc.bias"), resid=x, skip_period=Sc, out32=x1)
             # ---- spatial attention branch (vit.py:165-196)
@@ -207,9 +232,10 @@ class VisualEncoder:
             cls_o = buf("cls_o", (B * T, d), dt)
             lse = buf("lse", (B * T, heads, 1 + N), torch.float32)
             ops.seq_attn_fwd(qkv_s, None, o_s, cls_o, lse, 1 + N, B * T, heads, T, T, Sc, scale)
-            ops.cls_mean_fwd(cls_o, o_s, B, T, Sc, d)
+            ops.cls_mean_fwd(cls_o, o_s, B, T, Sc, d, dp["m_s"] if dp else None)
             x2 = buf("x2", (M, d), torch.float32)
-            ops.gemm16(o_s, w("attn.proj.weight"), bias=g("attn.proj.bias"), resid=x1, out32=x2)
+            ops.gemm16(o_s, w("attn.proj.weight"), bias=g("attn.proj.bias"), resid=x1, out32=x2,
+                       row_scale=dp["rsa"] if dp else None, row_scale_bias=dp["rsb"] if dp else None)
             # ---- MLP (vit.py:198-212)
             a_m = buf("a_m", (M, d), dt)
             st_m = buf("st_m", (2, M), torch.float32)
@@ -218,9 +244,10 @@ class VisualEncoder:
             pre = buf("pre", (M, 4 * d), dt) if save else None
             ops.gemm16(a_m, w("mlp.fc1.weight"), bias=g("mlp.fc1.bias"), act=ACT_GELU, out16=hdn, out16b=pre)
             x3 = buf("x3", (M, d), torch.float32) if save else x  # inference: write back into x
-            ops.gemm16(hdn, w("mlp.fc2.weight"), bias=g("mlp.fc2.bias"), resid=x2, out32=x3)
+            ops.gemm16(hdn, w("mlp.fc2.weight"), bias=g("mlp.fc2.bias"), resid=x2, out32=x3,
+                       row_scale=dp["rs_m"] if dp else None)
             if save:
-                ctx["blocks"].append(dict(x=x, a_t=a_t, st_t=st_t, qkv_t=qkv_t, o_t=o_t, p_t=p_t, x1=x1, a_s=a_s,
+                ctx["blocks"].append(dict(dp=dp, x=x, a_t=a_t, st_t=st_t, qkv_t=qkv_t, o_t=o_t, p_t=p_t, x1=x1, a_s=a_s,
                                           st_s=st_s, qkv_s=qkv_s, o_s=o_s, cls_o=cls_o, lse=lse, x2=x2, a_m=a_m, st_m=st_m,
                                           hdn=hdn,
                                           pre=pre))
@@ -251,9 +278,10 @@ class VisualEncoder:
         dx = _empty((M, d), torch.float32, dev)
         dx16 = _empty((M, d), dt, dev)
         last = f"{p}blocks.{self.depth - 1}."
+        dpl = ctx["blocks"][self.depth - 1]["dp"]
         ops.layernorm_bwd(dxn, ctx["x_final"], ctx["st_f"][0], ctx["st_f"][1], P[p + "norm.weight"].detach(), dx, 0,
                           dx16=dx16, dgamma=G[p + "norm.weight"], dbeta=G[p + "norm.bias"], param_scale=inv,
-                          colsum=G[last + "mlp.fc2.bias"])
+                          colsum=G[last + "mlp.fc2.bias"], dx16_row_scale=dpl["rs_m"] if dpl else None)
         del dxn
         d4 = _empty((M, 4 * d), dt, dev)
         d3 = _empty((M, 3 * d), dt, dev)
@@ -271,21 +299,24 @@ class VisualEncoder:
         for i in reversed(range(self.depth)):
             b = f"{p}blocks.{i}."
             c = ctx["blocks"][i]
+            dp = c["dp"]
+            dp_prev = ctx["blocks"][i - 1]["dp"] if i > 0 else None
             g = lambda n: P[b + n].detach()
             w = lambda n: W.get(b + n, P[b + n])
-            # ---- MLP
+            # ---- MLP (dx16 already carries this block's MLP stochastic-depth factor)
             ops.gemm16(dx16, w("mlp.fc2.weight"), b_layout=MNMAJOR, act=ACT_GELU_GRAD, aux=c["pre"], out16=d4)
             wgrad(dx16, c["hdn"], b + "mlp.fc2.weight")
             ops.gemm16(d4, w("mlp.fc1.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d4, c["a_m"], b + "mlp.fc1.weight", b + "mlp.fc1.bias")
             ops.layernorm_bwd(da, c["x2"], c["st_m"][0], c["st_m"][1], g("norm2.weight"), dx, 1, dx16=dx16,
                               dgamma=G[b + "norm2.weight"], dbeta=G[b + "norm2.bias"], param_scale=inv,
-                              colsum=G[b + "attn.proj.bias"])
+                              colsum=G[b + "attn.proj.bias"], dx16_row_scale=dp["rsa"] if dp else None,
+                              colsum_row_scale=dp["rsb"] if dp else None)
             # ---- spatial attention
             ops.gemm16(dx16, w("attn.proj.weight"), b_layout=MNMAJOR, out16=da)          # d o_s
             wgrad(dx16, c["o_s"], b + "attn.proj.weight")
             ops.seq_attn_bwd(c["qkv_s"], None, c["lse"], c["o_s"], c["cls_o"], da, d3, scratch, 1 + N, B * T, heads, T, T,
-                             Sc, scale)
+                             Sc, scale, cls_weight=dp["cls_w"] if dp else None)
             ops.gemm16(d3, w("attn.qkv.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d3, c["a_s"], b + "attn.qkv.weight", b + "attn.qkv.bias")
             # dx16 <- grad wrt x1 with cls rows zeroed (the temporal branch never touches cls rows)
@@ -293,7 +324,8 @@ class VisualEncoder:
                               zero_period=Sc, dgamma=G[b + "norm1.weight"], dbeta=G[b + "norm1.bias"],
                               param_scale=inv, colsum=G[b + "temporal_fc.bias"], colsum_zero_period=Sc)
             # ---- temporal attention
-            ops.gemm16(dx16, w("temporal_fc.weight"), b_layout=MNMAJOR, out16=da)        # d p_t
+            ops.gemm16(dx16, w("temporal_fc.weight"), b_layout=MNMAJOR, out16=da,        # d p_t
+                       row_scale=dp["rs_t"] if dp else None)
             wgrad(dx16, c["p_t"], b + "temporal_fc.weight")
             ops.gemm16(da, w("temporal_attn.proj.weight"), b_layout=MNMAJOR, out16=db_)  # d o_t
             wgrad(da, c["o_t"], b + "temporal_attn.proj.weight", b + "temporal_attn.proj.bias")
@@ -303,7 +335,8 @@ class VisualEncoder:
             nxt = G[f"{p}blocks.{i - 1}.mlp.fc2.bias"] if i > 0 else G[p + "patch_embed.proj.bias"]
             ops.layernorm_bwd(da, c["x"], c["st_t"][0], c["st_t"][1], g("temporal_norm1.weight"), dx, 1, dx16=dx16,
                               dgamma=G[b + "temporal_norm1.weight"], dbeta=G[b + "temporal_norm1.bias"],
-                              param_scale=inv, colsum=nxt, colsum_zero_period=0 if i > 0 else Sc)
+                              param_scale=inv, colsum=nxt, colsum_zero_period=0 if i > 0 else Sc,
+                              dx16_row_scale=dp_prev["rs_m"] if dp_prev else None)
             ctx["blocks"][i] = None  # release saved activations
         # ---- embeddings (vit.py:324-361) and patch projection
         pos_idx, tim_idx = ctx["pos_idx"], ctx["tim_idx"]
@@ -342,8 +375,13 @@ class BertEncoder:
         bq = W.get_cat(l + "qkv.b", [P[n + "bias"] for n in names])
         return Wq, bq
 
-    def embed(self, P, ids, save):
-        """BertEmbeddings (xbert.py:186-213): gather-sum then LayerNorm. Returns x32, x16, ctx."""
+    def _mask(self, shape, pdrop, seeds, dev):
+        m = _empty(shape, self.dtype, dev)
+        ops.dropout_mask(m, pdrop, next(seeds))
+        return m
+
+    def embed(self, P, ids, save, pdrop=0.0, seeds=None):
+        """BertEmbeddings (xbert.py:186-213): gather-sum, LayerNorm, dropout. Returns x32, x16, ctx."""
         e = self.p + "bert.embeddings."
         B, L = ids.shape
         dev = ids.device
@@ -355,22 +393,25 @@ class BertEncoder:
         x32 = _empty((B * L, h), torch.float32, dev)
         x16 = _empty((B * L, h), self.dtype, dev)
         st = _empty((2, B * L), torch.float32, dev)
+        mask = self._mask((B * L, h), pdrop, seeds, dev) if pdrop > 0 else None
         ops.layernorm_fwd(esum, P[e + "LayerNorm.weight"].detach(), P[e + "LayerNorm.bias"].detach(), self.eps,
-                          out32=x32, out16=x16, mean=st[0], rstd=st[1])
-        return x32, x16, (dict(ids=ids, esum=esum, st=st, L=L) if save else None)
+                          out32=x32, out16=x16, mean=st[0], rstd=st[1], mul16=mask)
+        return x32, x16, (dict(ids=ids, esum=esum, st=st, L=L, mask=mask) if save else None)
 
     def embed_backward(self, P, ctx, dx32, G, S):
         e = self.p + "bert.embeddings."
         h = self.h
         de = _empty(dx32.shape, torch.float32, dx32.device)
         ops.layernorm_bwd(dx32, ctx["esum"], ctx["st"][0], ctx["st"][1], P[e + "LayerNorm.weight"].detach(), de, 0,
-                          dgamma=G[e + "LayerNorm.weight"], dbeta=G[e + "LayerNorm.bias"], param_scale=1.0 / S)
+                          dgamma=G[e + "LayerNorm.weight"], dbeta=G[e + "LayerNorm.bias"], param_scale=1.0 / S,
+                          dy_mul16=ctx["mask"])
         ops.bert_embed_scatter(ctx["ids"].contiguous(), de, G[e + "word_embeddings.weight"],
                                G[e + "position_embeddings.weight"], G[e + "token_type_embeddings.weight"][0],
                                ctx["L"], h, 1.0 / S)
 
-    def forward(self, P, W, x32, x16, add_mask, nseq, S_len, mode, save):
-        """x32/x16: [nseq*S_len, h]; add_mask fp32 [nseq, S_len]. Returns (y32, y16, ctx)."""
+    def forward(self, P, W, x32, x16, add_mask, nseq, S_len, mode, save, pdrop=0.0, seeds=None):
+        """x32/x16: [nseq*S_len, h]; add_mask fp32 [nseq, S_len]. Returns (y32, y16, ctx).
+        pdrop > 0: train-mode hidden dropout after both dense output layers (xbert.py:358, 436)."""
         dev = x32.device
         h, heads, dt = self.h, self.heads, self.dtype
         M = nseq * S_len
@@ -388,8 +429,10 @@ class BertEncoder:
             lse = _empty((nseq, heads, S_len), torch.float32, dev)
             ops.seq_attn_fwd(qkv, add_mask, cx, None, lse, S_len, nseq, heads, 1, 1, S_len, scale)
             z1 = _empty((M, h), torch.float32, dev)
+            mo = self._mask((M, h), pdrop, seeds, dev) if pdrop > 0 else None
+            mf = self._mask((M, h), pdrop, seeds, dev) if pdrop > 0 else None
             ops.gemm16(cx, w("attention.output.dense.weight"), bias=g("attention.output.dense.bias"), resid=x32,
-                       out32=z1)
+                       out32=z1, act=ops.ACT_GELU_GRAD if mo is not None else 0, aux=mo)   # MUL_AUX: dropout mask
             a32 = _empty((M, h), torch.float32, dev)
             a16 = _empty((M, h), dt, dev)
             st1 = _empty((2, M), torch.float32, dev)
@@ -401,7 +444,8 @@ class BertEncoder:
             ops.gemm16(a16, w("intermediate.dense.weight"), bias=g("intermediate.dense.bias"), act=ACT_GELU, out16=hdn,
                        out16b=pre)
             z2 = _empty((M, h), torch.float32, dev)
-            ops.gemm16(hdn, w("output.dense.weight"), bias=g("output.dense.bias"), resid=a32, out32=z2)
+            ops.gemm16(hdn, w("output.dense.weight"), bias=g("output.dense.bias"), resid=a32, out32=z2,
+                       act=ops.ACT_GELU_GRAD if mf is not None else 0, aux=mf)
             y32 = _empty((M, h), torch.float32, dev)
             y16 = _empty((M, h), dt, dev)
             st2 = _empty((2, M), torch.float32, dev)
@@ -409,7 +453,7 @@ class BertEncoder:
                               out16=y16, mean=st2[0], rstd=st2[1])
             if save:
                 ctx["layers"].append(dict(i=i, x16=x16, qkv=qkv, cx=cx, lse=lse, z1=z1, st1=st1, a16=a16, hdn=hdn,
-                                          pre=pre, z2=z2, st2=st2))
+                                          pre=pre, z2=z2, st2=st2, mo=mo, mf=mf))
             x32, x16 = y32, y16
         return x32, x16, ctx
 
@@ -436,7 +480,8 @@ class BertEncoder:
             dz2_16 = _empty((M, h), dt, dev)
             ops.layernorm_bwd(dy32, c["z2"], c["st2"][0], c["st2"][1], g("output.LayerNorm.weight"), dz2, 0,
                               dx16=dz2_16, dgamma=G[l + "output.LayerNorm.weight"],
-                              dbeta=G[l + "output.LayerNorm.bias"], param_scale=inv, colsum=G[l + "output.dense.bias"])
+                              dbeta=G[l + "output.LayerNorm.bias"], param_scale=inv, colsum=G[l + "output.dense.bias"],
+                              dx16_mul16=c["mf"])
             du = _empty((M, ff), dt, dev)
             ops.gemm16(dz2_16, w("output.dense.weight"), b_layout=MNMAJOR, act=ACT_GELU_GRAD, aux=c["pre"], out16=du)
             wgrad(dz2_16, c["hdn"], G[l + "output.dense.weight"])
@@ -448,7 +493,7 @@ class BertEncoder:
             ops.layernorm_bwd(da32, c["z1"], c["st1"][0], c["st1"][1], g("attention.output.LayerNorm.weight"), dz1, 0,
                               dx16=dz1_16, dgamma=G[l + "attention.output.LayerNorm.weight"],
                               dbeta=G[l + "attention.output.LayerNorm.bias"], param_scale=inv,
-                              colsum=G[l + "attention.output.dense.bias"])
+                              colsum=G[l + "attention.output.dense.bias"], dx16_mul16=c["mo"])
             dcx = _empty((M, h), dt, dev)
             ops.gemm16(dz1_16, w("attention.output.dense.weight"), b_layout=MNMAJOR, out16=dcx)
             wgrad(dz1_16, c["cx"], G[l + "attention.output.dense.weight"])
@@ -506,6 +551,8 @@ class AlproEngine:
         self.sampler = multinomial_sampler
         self.comm = LocalComm()
         self.last_grads = None
+        self.base_seed = 0x5DEECE66
+        self._step = 0
 
     # ------------------------------------------------------------------------------------------------ features
     def _proj_norm(self, P, x, ldx, wname, rows):
@@ -523,8 +570,19 @@ class AlproEngine:
         return ((1.0 - mask.to(torch.float32)) * -10000.0).contiguous()
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, P, batch, need_grad=True):
-        """Returns (outputs, ctx). outputs mirrors the reference dict (alpro_models.py:172-183, 793-798)."""
+    def _seed_stream(self):
+        """Python-side stream of 32-bit seeds for the dropout sites of one forward pass (no device sync)."""
+        self._step += 1
+        base = (self.base_seed * 0x9E3779B1 + self._step * 0x85EBCA77) & 0xFFFFFFFF
+        site = 0
+        while True:
+            site += 1
+            yield (base ^ (site * 0xC2B2AE3D)) & 0xFFFFFFFF
+
+    def forward(self, P, batch, need_grad=True, training=False):
+        """Returns (outputs, ctx). outputs mirrors the reference dict (alpro_models.py:172-183, 793-798).
+        training=True applies the reference's train-mode regularisers: BERT hidden dropout (xbert.py:178,358,436) and
+        TimeSformer stochastic depth (vit.py:157,181,212). Attention-probability dropout (xbert.py:331) is not applied."""
         kind = self.kind
         dev = batch["visual_inputs"].device
         cfg, h, d = self.cfg, self.cfg["hidden_size"], self.vis["d"]
@@ -533,7 +591,10 @@ class AlproEngine:
         ops.clamp_scalar(P["temp"].detach(), 0.001, 0.5)                       # temp.clamp_ :80-81 / :734-735
         frames = batch["visual_inputs"]
         B = frames.shape[0]
-        ve, vctx = self.visual.forward(P, self.W, frames, save)                 # [B, Nv, d]
+        pdrop = float(cfg.get("hidden_dropout_prob", 0.0)) if training else 0.0
+        dpr = float(self.vis.get("drop_path_rate", 0.0)) if training else 0.0
+        seeds = self._seed_stream() if pdrop > 0 else None
+        ve, vctx = self.visual.forward(P, self.W, frames, save, drop_path_rate=dpr)     # [B, Nv, d]
         Nv = ve.shape[1]
         ids, mask = batch["text_input_ids"], batch["text_input_mask"]
         L = ids.shape[1]
@@ -546,8 +607,9 @@ class AlproEngine:
             ids_all, mask_all = ids, mask
         nt = ids_all.shape[0]
         mask_all = mask_all.contiguous()
-        x32, x16, ectx = self.bert.embed(P, ids_all, save)
-        te, _, tctx = self.bert.forward(P, self.W, x32, x16, self._text_mask_add(mask_all), nt, L, "text", save)
+        x32, x16, ectx = self.bert.embed(P, ids_all, save, pdrop, seeds)
+        te, _, tctx = self.bert.forward(P, self.W, x32, x16, self._text_mask_add(mask_all), nt, L, "text", save, pdrop,
+                                        seeds)
         te = te.view(nt, L, h)
 
         # ---- VTC (alpro_models.py:103-128, 750-779)
@@ -591,7 +653,7 @@ class AlproEngine:
         f16 = _empty((S_all * R, h), self.dtype, dev)
         fmask = _empty((S_all, R), torch.float32, dev)
         ops.fusion_gather_fwd(te, ve, mask_all, ti, vi, f32, f16, fmask, S_all, L, Nv, h)
-        fo, _, fctx = self.bert.forward(P, self.W, f32, f16, fmask, S_all, R, "fusion", save)   # [S_all*R, h]
+        fo, _, fctx = self.bert.forward(P, self.W, f32, f16, fmask, S_all, R, "fusion", save, pdrop, seeds)
 
         # ---- VTM head (alpro_models.py:334-339)
         itm_scores = _empty((3 * B, 2), torch.float32, dev)
@@ -608,6 +670,7 @@ class AlproEngine:
                        fctx=fctx, fo=fo, ti=ti, vi=vi, vf=vf, vnorm=vnorm, tf=tf, tnorm=tnorm, gv=gv, gt=gt,
                        sim_v2t=sim_v2t, sim_t2v=sim_t2v, ce_v=ce_v, ce_t=ce_t, vtc_labels=vtc_labels,
                        itm_scores=itm_scores, itm_labels=itm_labels, ce_itm=ce_itm, use_mlm=use_mlm, use_mpm=use_mpm)
+        self.last_ctx = ctx   # introspection hook for the train-mode parity tests (regulariser masks live in ctx)
         out["_neg_video"], out["_neg_text"] = neg_video, neg_text
         out["_video_embeds"], out["_text_embeds"] = ve, te[:B]
 

@@ -34,7 +34,8 @@ def _vis_from_cfg(video_enc_cfg, d=768, depth=12, heads=12):
     configuration (embed_dim/depth/num_heads)."""
     return dict(d=video_enc_cfg.get("embed_dim", d), depth=video_enc_cfg.get("depth", depth),
                 heads=video_enc_cfg.get("num_heads", heads), T=video_enc_cfg["num_frm"],
-                img=video_enc_cfg["img_size"], patch=video_enc_cfg["patch_size"])
+                img=video_enc_cfg["img_size"], patch=video_enc_cfg["patch_size"],
+                drop_path_rate=float(video_enc_cfg.get("drop_path_rate", 0.0)))
 
 
 class _Holder(nn.Module):
@@ -94,7 +95,7 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, batch, names, need, *params):
         P = model._tensor_dict()
-        out, ectx = model.engine.forward(P, batch, need_grad=need)
+        out, ectx = model.engine.forward(P, batch, need_grad=need, training=model.training)
         ctx.model, ctx.ectx, ctx.names = model, ectx, names
         ctx.loss_keys = [k for k in ("itc_loss", "itm_loss", "mlm_loss", "mpm_loss") if out.get(k) is not None]
         model._last_out = out

@@ -43,7 +43,7 @@ def _row_major_2d(t, name):
 
 
 def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, aux=None, resid=None, out32=None,
-           out16=None, out16b=None, skip_period=0, split_k=0, alpha=1.0):
+           out16=None, out16b=None, skip_period=0, split_k=0, alpha=1.0, row_scale=None, row_scale_bias=None):
     """acc[m,n] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, fused epilogue (see include/alpro_b200.h).
 
     a: [M,K] (K-major) or [K,M] (MN-major) 16-bit; b: [N,K] (K-major) or [K,N] (MN-major) 16-bit.
@@ -92,6 +92,8 @@ def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, a
     ep.skip_period = skip_period
     ep.split_k = split_k
     ep.alpha = alpha
+    ep.row_scale_acc = _ptr(row_scale)
+    ep.row_scale_bias = _ptr(row_scale_bias)
     prof = GEMM_PROFILE
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -124,22 +126,28 @@ def cast16(src, dst):
     check(_L.alpro_cast_f32_to_16(_p(src), _p(dst), src.numel(), _fmt(dst), _s()), "alpro_cast_f32_to_16")
 
 
-def layernorm_fwd(x, gamma, beta, eps, out32=None, out16=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps, out32=None, out16=None, mean=None, rstd=None, mul16=None):
     M, d = x.shape
     check(_L.alpro_layernorm_fwd(_p(x), x.stride(0), _p(gamma), _p(beta), eps, M, d, _p(out32),
                                  out32.stride(0) if out32 is not None else 0, _p(out16),
                                  out16.stride(0) if out16 is not None else 0,
-                                 _fmt(out16) if out16 is not None else 0, _p(mean), _p(rstd), _s()), "alpro_layernorm_fwd")
+                                 _fmt(out16) if out16 is not None else (_fmt(mul16) if mul16 is not None else 0),
+                                 _p(mean), _p(rstd), _p(mul16), mul16.stride(0) if mul16 is not None else 0, _s()),
+          "alpro_layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx32, accumulate, dx16=None, zero_period=0, dgamma=None, dbeta=None,
-                  param_scale=1.0, colsum=None, colsum_zero_period=0):
+                  param_scale=1.0, colsum=None, colsum_zero_period=0, dy_mul16=None, dx16_mul16=None,
+                  dx16_row_scale=None, colsum_row_scale=None):
     M, d = x.shape
     check(_L.alpro_layernorm_bwd(_p(dy), _KIND[dy.dtype], dy.stride(0), _p(x), x.stride(0), _p(mean), _p(rstd),
                                  _p(gamma), M, d, _p(dx32), dx32.stride(0), int(accumulate), _p(dx16),
-                                 dx16.stride(0) if dx16 is not None else 0, _fmt(dx16) if dx16 is not None else 0,
+                                 dx16.stride(0) if dx16 is not None else 0,
+                                 _fmt(dx16) if dx16 is not None else (_fmt(dy_mul16) if dy_mul16 is not None else 0),
                                  zero_period, _p(dgamma), _p(dbeta), param_scale, _p(colsum), colsum_zero_period,
-                                 _s()), "alpro_layernorm_bwd")
+                                 _p(dy_mul16), dy_mul16.stride(0) if dy_mul16 is not None else 0, _p(dx16_mul16),
+                                 dx16_mul16.stride(0) if dx16_mul16 is not None else 0, _p(dx16_row_scale),
+                                 _p(colsum_row_scale), _s()), "alpro_layernorm_bwd")
 
 
 def colsum(x, out, alpha=1.0, zero_period=0):
@@ -190,8 +198,13 @@ def fusion_gather_bwd(dout, ti, vi, dtext, dvideo, S, L, Nv, h):
           "alpro_fusion_gather_bwd")
 
 
-def cls_mean_fwd(cls_t, o, B, T, clip_rows, d):
-    check(_L.alpro_cls_mean_fwd(_p(cls_t), _p(o), o.stride(0), _fmt(o), B, T, clip_rows, d, _s()), "alpro_cls_mean_fwd")
+def cls_mean_fwd(cls_t, o, B, T, clip_rows, d, frame_weight=None):
+    check(_L.alpro_cls_mean_fwd(_p(cls_t), _p(o), o.stride(0), _fmt(o), B, T, clip_rows, d, _p(frame_weight), _s()),
+          "alpro_cls_mean_fwd")
+
+
+def dropout_mask(out16, p, seed):
+    check(_L.alpro_dropout_mask(_p(out16), _fmt(out16), out16.numel(), p, seed & 0xffffffff, _s()), "alpro_dropout_mask")
 
 
 def temporal_attn_fwd(qkv, out, B, N, T, heads, scale):
@@ -209,9 +222,10 @@ def seq_attn_fwd(qkv, mask, o, cls_o, lse, S, nseq, heads, seq_div, stride, clip
                                 heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()), "alpro_seq_attn_fwd")
 
 
-def seq_attn_bwd(qkv, mask, lse, o_fwd, cls_fwd, dout, dqkv, scratch, S, nseq, heads, seq_div, stride, clip_rows, scale):
+def seq_attn_bwd(qkv, mask, lse, o_fwd, cls_fwd, dout, dqkv, scratch, S, nseq, heads, seq_div, stride, clip_rows, scale,
+                 cls_weight=None):
     assert o_fwd.stride(0) == dout.stride(0)
-    check(_L.alpro_seq_attn_bwd(_p(qkv), qkv.stride(0), _p(mask), _p(lse), _p(o_fwd), _p(cls_fwd), _p(dout),
+    check(_L.alpro_seq_attn_bwd(_p(qkv), qkv.stride(0), _p(mask), _p(lse), _p(o_fwd), _p(cls_fwd), _p(cls_weight), _p(dout),
                                 dout.stride(0), _p(dqkv),
                                 _p(scratch), S, nseq, heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()),
           "alpro_seq_attn_bwd")

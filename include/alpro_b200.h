@@ -34,6 +34,7 @@ extern "C" {
 #define ALPRO_ACT_NONE 0
 #define ALPRO_ACT_GELU 1      /* out = gelu_erf(acc + bias); out16b (optional) = gelu'(acc + bias)   (nn.GELU, vit.py:50,61; ACT2FN['gelu'] xbert.py:417) */
 #define ALPRO_ACT_GELU_GRAD 2 /* out = acc * aux, aux = the gelu' saved by ALPRO_ACT_GELU               (autograd of the above) */
+#define ALPRO_ACT_MUL_AUX 2   /* alias: out = (acc + bias) * aux      (nn.Dropout mask/keep multiply, xbert.py:358,436) */
 #define ALPRO_ACT_RELU 3
 #define ALPRO_ACT_RELU_GRAD 4 /* out = acc * (aux > 0) */
 
@@ -73,6 +74,9 @@ typedef struct AlproGemmEpilogue {
                             epilogue is out32 += alpha*acc with fp32 red.global.add (caller zeroes / pre-loads out32);
                             bias/act/resid/out16 must be unset. Used for weight-gradient contractions (K = #tokens). */
   float alpha;
+  const float* row_scale_acc;  /* optional [M]: v = row_scale_acc[m]*alpha*acc + row_scale_bias[m]*bias   (DropPath: the
+                                  per-sample mask/keep_prob of vit_utils.py:137-162 expanded to token rows) */
+  const float* row_scale_bias; /* optional [M]; defaults to row_scale_acc */
 } AlproGemmEpilogue;
 
 int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
@@ -85,18 +89,24 @@ int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, 
 int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int fmt, void* stream);
 
 /* LayerNorm over the last dim (nn.LayerNorm: vit.py:113,119,127,279 eps 1e-6; xbert.py:177,354,433,658 eps 1e-12).
- * x fp32 [M,d] -> out32 (optional) and/or out16 (optional); per-row mean / rstd saved for the backward. d%4==0, d<=1024 */
+ * x fp32 [M,d] -> out32 (optional) and/or out16 (optional); per-row mean / rstd saved for the backward. d%4==0, d<=1024.
+ * mul16 (optional, same 16-bit format as out16): dropout mask/keep multiplied into the outputs. */
 int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int64_t M, int d,
                         float* out32, int64_t ld32, void* out16, int64_t ld16, int out16_fmt, float* mean, float* rstd,
-                        void* stream);
+                        const void* mul16, int64_t ldmul, void* stream);
 /* dy_kind 0 fp32 / 1 fp16 / 2 bf16. dx32 = (accumulate ? dx32 : 0) + LN'(dy); dx16 = 16-bit copy of the resulting dx32
  * (rows with row % zero_period == 0 written as zero when zero_period > 0). dgamma/dbeta += param_scale * sums (atomics).
  * colsum (optional) += param_scale * column sums of the resulting dx over rows with row % colsum_zero_period != 0: the
- * bias gradient of the Linear layer whose output gradient this dx is (saves a separate pass over dx). */
+ * bias gradient of the Linear layer whose output gradient this dx is (saves a separate pass over dx).
+ * Train-mode hooks (all optional): dy_mul16 = dropout mask on this LayerNorm's output; dx16_mul16 / dx16_row_scale =
+ * dropout mask / DropPath row factor of the branch whose output gradient dx16 is; colsum_row_scale overrides the row
+ * factor for the bias column sums. Masks use the 16-bit format of dx16. */
 int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, const float* x, int64_t ldx, const float* mean,
                         const float* rstd, const float* gamma, int64_t M, int d, float* dx32, int64_t lddx,
                         int accumulate, void* dx16, int64_t lddx16, int dx16_fmt, int zero_period, float* dgamma,
-                        float* dbeta, float param_scale, float* colsum, int colsum_zero_period, void* stream);
+                        float* dbeta, float param_scale, float* colsum, int colsum_zero_period, const void* dy_mul16,
+                        int64_t lddymul, const void* dx16_mul16, int64_t lddxmul, const float* dx16_row_scale,
+                        const float* colsum_row_scale, void* stream);
 /* out[n] += alpha * sum_m x[m,n]; kind 0 fp32 / 1 fp16 / 2 bf16 (bias gradients of every nn.Linear on the path) */
 int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int N, float* out, float alpha, int zero_period,
                  void* stream);
@@ -124,7 +134,10 @@ int alpro_fusion_gather_fwd(const float* text, const float* video, const int64_t
 int alpro_fusion_gather_bwd(const float* dout, const int32_t* ti, const int32_t* vi, float* dtext, float* dvideo, int S,
                             int L, int Nv, int h, void* stream);
 /* mean over the T per-frame cls outputs [B,T,d] -> canonical cls row b*S of o (Block.forward vit.py:184-187) */
-int alpro_cls_mean_fwd(const void* cls_t, void* o, int64_t ldo, int fmt, int B, int T, int S, int d, void* stream);
+int alpro_cls_mean_fwd(const void* cls_t, void* o, int64_t ldo, int fmt, int B, int T, int S, int d,
+                       const float* frame_weight, void* stream);
+/* out[i] = keep_i/(1-p), keep_i ~ Bernoulli(1-p) from a stateless counter hash of (seed, i) (nn.Dropout sites xbert.py:178,358,436) */
+int alpro_dropout_mask(void* out16, int fmt, int64_t n, float p, uint32_t seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Attention (alpro_b200/csrc/attention.cu), head_dim = 64
@@ -142,9 +155,11 @@ int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const void* dout, i
 int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* mask, void* o, int64_t ld_o, void* cls_o, float* lse,
                        int S, int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
                        void* stream);
-/* backward: o_fwd = the forward output rows, cls_fwd = the forward per-sequence token-0 outputs (cls_o, seq_div > 1 only) */
+/* backward: o_fwd = the forward output rows, cls_fwd = the forward per-sequence token-0 outputs (cls_o, seq_div > 1 only),
+ * cls_weight (optional [nseq]) = weight of each frame's cls output in the group's cls row (default 1/seq_div) */
 int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* o_fwd,
-                       const void* cls_fwd, const void* dout, int64_t ld_o, void* dqkv, float* dcls_qkv_scratch, int S,
+                       const void* cls_fwd, const float* cls_weight, const void* dout, int64_t ld_o, void* dqkv,
+                       float* dcls_qkv_scratch, int S,
                        int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------

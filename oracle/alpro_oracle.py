@@ -35,8 +35,10 @@ def _mha(x, wqkv, bqkv, wproj, bproj, heads):
     return F.linear(o, wproj, bproj)
 
 
-def vit_block(sd, p, x, B, T, heads, eps=1e-6):
-    """Block.forward (divided_space_time), vit.py:136-213, eval mode (drop_path = identity).
+def vit_block(sd, p, x, B, T, heads, eps=1e-6, dp=None):
+    """Block.forward (divided_space_time), vit.py:136-213. dp=None: eval mode (drop_path = identity); otherwise a dict
+    of per-sample DropPath factors mask/keep_prob (vit_utils.py:137-162) injected by the test: m_t [B,N] (temporal
+    branch, mask shape (b h w,1,1)), m_s [B,T] (spatial, (b t,1,1)), m_m [B] (MLP, (b,1,1)).
     x: [B, 1 + N*T, d] with token index 1 + n*T + t ('b (h w t) m', vit.py:147)."""
     d = x.shape[-1]
     N = (x.shape[1] - 1) // T
@@ -46,6 +48,8 @@ def vit_block(sd, p, x, B, T, heads, eps=1e-6):
     t_in = F.layer_norm(xt, (d,), g("temporal_norm1.weight"), g("temporal_norm1.bias"), eps)
     t_out = _mha(t_in, g("temporal_attn.qkv.weight"), g("temporal_attn.qkv.bias"), g("temporal_attn.proj.weight"),
                  g("temporal_attn.proj.bias"), heads)
+    if dp is not None:
+        t_out = t_out * dp["m_t"].reshape(B * N, 1, 1)                    # res_temporal = drop_path(...), vit.py:157
     t_out = F.linear(t_out.reshape(B, N * T, d), g("temporal_fc.weight"), g("temporal_fc.bias"))
     xt = x[:, 1:, :] + t_out
     # spatial attention over cls + N patches of each frame (vit.py:165-191)
@@ -55,13 +59,18 @@ def vit_block(sd, p, x, B, T, heads, eps=1e-6):
     xs = torch.cat([cls_rep, xs], dim=1)
     s_in = F.layer_norm(xs, (d,), g("norm1.weight"), g("norm1.bias"), eps)
     s_out = _mha(s_in, g("attn.qkv.weight"), g("attn.qkv.bias"), g("attn.proj.weight"), g("attn.proj.bias"), heads)
+    if dp is not None:
+        s_out = s_out * dp["m_s"].reshape(B * T, 1, 1)                    # res_spatial = drop_path(...), vit.py:181
     cls_out = s_out[:, 0, :].reshape(B, T, d).mean(dim=1, keepdim=True)   # vit.py:184-187
     res = s_out[:, 1:, :].reshape(B, T, N, d).permute(0, 2, 1, 3).reshape(B, N * T, d)
     x = torch.cat([cls0, xt], dim=1) + torch.cat([cls_out, res], dim=1)    # vit.py:195-196
     # MLP (vit.py:198-212, Mlp.forward :59-65)
     m_in = F.layer_norm(x, (d,), g("norm2.weight"), g("norm2.bias"), eps)
     hdn = F.gelu(F.linear(m_in, g("mlp.fc1.weight"), g("mlp.fc1.bias")))
-    return x + F.linear(hdn, g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+    m_out = F.linear(hdn, g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+    if dp is not None:
+        m_out = m_out * dp["m_m"].reshape(B, 1, 1)                        # x_res + drop_path(mlp_out), vit.py:212
+    return x + m_out
 
 
 def vit_tokens(sd, p, frames, patch):
@@ -91,13 +100,13 @@ def vit_tokens(sd, p, frames, patch):
     return torch.cat([cls.expand(B, 1, d), y], dim=1)
 
 
-def visual_forward(sd, p, frames, vis, return_tokens=False):
+def visual_forward(sd, p, frames, vis, return_tokens=False, drop_path=None):
     """TimeSformer.forward_features vit.py:475-503 (pooling='temporal'): blocks, final LN (vit.py:372), mean over t.
     p is the prefix of the VisionTransformer ('visual_encoder.model.'). Returns [B, 1+N, d]."""
     B, T = frames.shape[:2]
     x = vit_tokens(sd, p, frames, vis["patch"])
     for i in range(vis["depth"]):
-        x = vit_block(sd, f"{p}blocks.{i}.", x, B, T, vis["heads"])
+        x = vit_block(sd, f"{p}blocks.{i}.", x, B, T, vis["heads"], dp=drop_path[i] if drop_path else None)
     d = x.shape[-1]
     x = F.layer_norm(x, (d,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
     N = (x.shape[1] - 1) // T
@@ -109,17 +118,19 @@ def visual_forward(sd, p, frames, vis, return_tokens=False):
 # --------------------------------------------------------------------------------------------------------------
 # BERT (text / fusion modes)                    src/modeling/xbert.py
 # --------------------------------------------------------------------------------------------------------------
-def bert_embeddings(sd, p, ids, eps):
-    """BertEmbeddings.forward xbert.py:186-213 (token_type all zero, absolute positions, eval: no dropout)."""
+def bert_embeddings(sd, p, ids, eps, mask=None):
+    """BertEmbeddings.forward xbert.py:186-213 (token_type all zero, absolute positions). mask: injected dropout
+    mask/keep for train-mode parity (None = eval)."""
     e = p + "bert.embeddings."
     L = ids.shape[1]
     x = sd[e + "word_embeddings.weight"][ids] + sd[e + "token_type_embeddings.weight"][0] \
         + sd[e + "position_embeddings.weight"][:L].unsqueeze(0)
     h = x.shape[-1]
-    return F.layer_norm(x, (h,), sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], eps)
+    y = F.layer_norm(x, (h,), sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], eps)
+    return y if mask is None else y * mask.reshape(y.shape)
 
 
-def bert_layer(sd, l, x, ext_mask, heads, eps):
+def bert_layer(sd, l, x, ext_mask, heads, eps, drop=None):
     """BertLayer.forward xbert.py:457-519 = BertSelfAttention :263-346 + BertSelfOutput :349-360 +
     BertIntermediate :412-424 + BertOutput :427-438 (post-LN; has_cross_attention=False :450)."""
     Bp, S, h = x.shape
@@ -131,24 +142,29 @@ def bert_layer(sd, l, x, ext_mask, heads, eps):
     scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh) + ext_mask           # xbert.py:317-320
     ctx = (torch.softmax(scores, dim=-1) @ v).transpose(1, 2).reshape(Bp, S, h)
     a = F.linear(ctx, sd[l + "attention.output.dense.weight"], sd[l + "attention.output.dense.bias"])
+    if drop is not None:
+        a = a * drop[0].reshape(a.shape)                                    # BertSelfOutput.dropout, xbert.py:358
     a = F.layer_norm(a + x, (h,), sd[l + "attention.output.LayerNorm.weight"], sd[l + "attention.output.LayerNorm.bias"], eps)
     i = F.gelu(F.linear(a, sd[l + "intermediate.dense.weight"], sd[l + "intermediate.dense.bias"]))
     o = F.linear(i, sd[l + "output.dense.weight"], sd[l + "output.dense.bias"])
+    if drop is not None:
+        o = o * drop[1].reshape(o.shape)                                    # BertOutput.dropout, xbert.py:436
     return F.layer_norm(o + a, (h,), sd[l + "output.LayerNorm.weight"], sd[l + "output.LayerNorm.bias"], eps)
 
 
-def bert_encode(sd, p, x, mask, cfg, mode):
+def bert_encode(sd, p, x, mask, cfg, mode, drops=None):
     """BertModel.forward xbert.py:940-1081 + BertEncoder.forward :528-630: extended mask (1-mask)*-10000
     (get_extended_attention_mask :878-938), layers [0,fusion_layer) for 'text', [fusion_layer,L) for 'fusion'."""
     ext = (1.0 - mask.to(torch.float32))[:, None, None, :] * -10000.0
     lo, hi = (0, cfg["fusion_layer"]) if mode == "text" else (cfg["fusion_layer"], cfg["num_hidden_layers"])
     for i in range(lo, hi):
-        x = bert_layer(sd, f"{p}bert.encoder.layer.{i}.", x, ext, cfg["num_attention_heads"], cfg["layer_norm_eps"])
+        x = bert_layer(sd, f"{p}bert.encoder.layer.{i}.", x, ext, cfg["num_attention_heads"], cfg["layer_norm_eps"],
+                       drop=drops[i] if drops else None)
     return x
 
 
-def bert_text(sd, p, ids, mask, cfg):
-    return bert_encode(sd, p, bert_embeddings(sd, p, ids, cfg["layer_norm_eps"]), mask, cfg, "text")
+def bert_text(sd, p, ids, mask, cfg, emb_mask=None, drops=None):
+    return bert_encode(sd, p, bert_embeddings(sd, p, ids, cfg["layer_norm_eps"], emb_mask), mask, cfg, "text", drops)
 
 
 def mlm_head(sd, p, x, eps):
@@ -197,7 +213,7 @@ def mine_negatives(sim_v2t, sim_t2v, rank, sampler):
     return neg_video, neg_text
 
 
-def vtm(sd, pfx, cfg, text_embeds, text_mask, video_embeds, neg_video, neg_text):
+def vtm(sd, pfx, cfg, text_embeds, text_mask, video_embeds, neg_video, neg_text, drops_pos=None, drops_neg=None):
     """compute_vtm (alpro_models.py:269-344, 800-872): fusion encoder on positives (text_i, video_i), then on
     (text_i, video_neg_i) and (text_neg_i, video_i); itm_head on the [CLS] outputs; CE with labels [1]*b + [0]*2b.
     Returns loss, logits [3b,2], labels, positive fusion output [b, L+1+N, h]."""
@@ -208,27 +224,30 @@ def vtm(sd, pfx, cfg, text_embeds, text_mask, video_embeds, neg_video, neg_text)
     nti = torch.tensor(neg_text, dtype=torch.long)
     emb_pos = torch.cat([text_embeds, video_embeds], dim=1)
     mask_pos = torch.cat([text_mask, ones], dim=1)
-    out_pos = bert_encode(sd, pfx + "text_encoder.", emb_pos, mask_pos, cfg, "fusion")
+    out_pos = bert_encode(sd, pfx + "text_encoder.", emb_pos, mask_pos, cfg, "fusion", drops_pos)
     txt_all = torch.cat([text_embeds, text_embeds[nti]], dim=0)
     msk_all = torch.cat([text_mask, text_mask[nti]], dim=0)
     vid_all = torch.cat([video_embeds[nvi], video_embeds], dim=0)
     emb_neg = torch.cat([txt_all, vid_all], dim=1)
     mask_neg = torch.cat([msk_all, torch.cat([ones, ones], dim=0)], dim=1)
-    out_neg = bert_encode(sd, pfx + "text_encoder.", emb_neg, mask_neg, cfg, "fusion")
+    out_neg = bert_encode(sd, pfx + "text_encoder.", emb_neg, mask_neg, cfg, "fusion", drops_neg)
     cls = torch.cat([out_pos[:, 0], out_neg[:, 0]], dim=0)
     logits = F.linear(cls, sd[pfx + "itm_head.weight"], sd[pfx + "itm_head.bias"])
     labels = torch.cat([torch.ones(b, dtype=torch.long), torch.zeros(2 * b, dtype=torch.long)])
     return F.cross_entropy(logits, labels), logits, labels, out_pos
 
 
-def retrieval_forward(sd, cfg, vis, batch, rank=0, gather=None, sampler=argmax_sampler):
-    """AlproForVideoTextRetrieval.forward alpro_models.py:733-798."""
-    video_embeds = visual_forward(sd, "visual_encoder.model.", batch["visual_inputs"], vis)
-    text_embeds = bert_text(sd, "text_encoder.", batch["text_input_ids"], batch["text_input_mask"], cfg)
+def retrieval_forward(sd, cfg, vis, batch, rank=0, gather=None, sampler=argmax_sampler, train=None):
+    """AlproForVideoTextRetrieval.forward alpro_models.py:733-798. `train` (tests only): injected regulariser masks
+    dict(drop_path=[per-block dict], emb=mask, text={layer: (mo, mf)}, pos={layer: ...}, neg={layer: ...})."""
+    tr = train or {}
+    video_embeds = visual_forward(sd, "visual_encoder.model.", batch["visual_inputs"], vis, drop_path=tr.get("drop_path"))
+    text_embeds = bert_text(sd, "text_encoder.", batch["text_input_ids"], batch["text_input_mask"], cfg,
+                            tr.get("emb"), tr.get("text"))
     itc_loss, s_v2t, s_t2v, vf, tf = vtc(sd, "", video_embeds[:, 0], text_embeds[:, 0], rank, gather)
     neg_v, neg_t = mine_negatives(s_v2t.detach(), s_t2v.detach(), rank, sampler)
     itm_loss, itm_scores, itm_labels, _ = vtm(sd, "", cfg, text_embeds, batch["text_input_mask"], video_embeds,
-                                              neg_v, neg_t)
+                                              neg_v, neg_t, tr.get("pos"), tr.get("neg"))
     return dict(itm_scores=itm_scores, itm_loss=itm_loss, itm_labels=itm_labels, itc_loss=itc_loss,
                 _video_embeds=video_embeds, _text_embeds=text_embeds, _neg_video=neg_v, _neg_text=neg_t,
                 _video_feat=vf, _text_feat=tf)

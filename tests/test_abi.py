@@ -45,9 +45,10 @@ def test_epilogue_struct_layout_matches_header(built):
 #include <stddef.h>
 #include "alpro_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(AlproGemmEpilogue), offsetof(AlproGemmEpilogue, ld32),
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(AlproGemmEpilogue), offsetof(AlproGemmEpilogue, ld32),
          offsetof(AlproGemmEpilogue, out16_fmt), offsetof(AlproGemmEpilogue, act),
-         offsetof(AlproGemmEpilogue, split_k), offsetof(AlproGemmEpilogue, alpha));
+         offsetof(AlproGemmEpilogue, split_k), offsetof(AlproGemmEpilogue, alpha),
+         offsetof(AlproGemmEpilogue, row_scale_bias));
   return 0;
 }'''
     import tempfile
@@ -58,7 +59,8 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         vals = [int(x) for x in subprocess.check_output([exe], text=True).split()]
     E = _lib.GemmEpilogue
-    assert vals == [ctypes.sizeof(E), E.ld32.offset, E.out16_fmt.offset, E.act.offset, E.split_k.offset, E.alpha.offset]
+    assert vals == [ctypes.sizeof(E), E.ld32.offset, E.out16_fmt.offset, E.act.offset, E.split_k.offset, E.alpha.offset,
+                    E.row_scale_bias.offset]
 
 
 def test_modules_keep_reference_state_dict_schema():
