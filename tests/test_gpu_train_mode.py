@@ -119,8 +119,8 @@ def test_train_mode_step_matches_oracle_with_injected_masks():
     model.train()
     torch.manual_seed(123)
     out = model(to_cuda(batch))
+    tr = _collect_train_masks(model, cfg)      # before backward: the step context is released block by block
     (out["itc_loss"] + out["itm_loss"]).backward()
-    tr = _collect_train_masks(model, cfg)
     assert any(d is not None for d in tr["drop_path"])          # stochastic depth really was active
     assert float((tr["emb"] == 0).float().mean()) > 0.05         # and so was dropout
     # eval-mode result must differ (the regularisers do something) ...
