@@ -13,6 +13,7 @@
 // Backward kernels recompute the probabilities from the saved log-sum-exp (no SxS tensor ever reaches HBM).
 #include "common.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace alpro {
 namespace {
@@ -276,7 +277,20 @@ struct SAttnParams {
   int seq_div, stride;   // row(seq, j) = (seq / seq_div) * clip_rows + (j == 0 ? 0 : 1 + seq % seq_div + (j-1) * stride)
   long long clip_rows;
   float scale;
+  // train-mode attention-probability dropout (BertSelfAttention.dropout, xbert.py:331): 0 = off
+  uint32_t drop_thr, drop_seed;
+  float drop_scale;
 };
+
+// mask/keep factors of the key pair (2*jp, 2*jp+1) for query row i of (seq, head): one counter-hash per pair
+__device__ __forceinline__ void drop_pair(const SAttnParams& p, int S_pad, int seq, int head, int i, int jp, float& m0,
+                                          float& m1) {
+  const uint64_t idx = (static_cast<uint64_t>(seq) * p.heads + head) * S_pad * (S_pad >> 1) +
+                       static_cast<uint64_t>(i) * (S_pad >> 1) + jp;
+  const uint32_t h = rand16x2(p.drop_seed, idx);
+  m0 = (h & 0xffff) >= p.drop_thr ? p.drop_scale : 0.f;
+  m1 = (h >> 16) >= p.drop_thr ? p.drop_scale : 0.f;
+}
 
 __device__ __forceinline__ long long srow(const SAttnParams& p, int seq, int j) {
   const long long base = static_cast<long long>(seq / p.seq_div) * p.clip_rows;
@@ -415,6 +429,17 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    if (p.drop_thr) {   // dropout acts on the probabilities that multiply V; the row sums above stay undropped
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (EXACT || n < nt) {
+          float a0, a1, b0, b1;
+          drop_pair(p, S_pad, seq, head, qt * 16 + g, n * 4 + t, a0, a1);
+          drop_pair(p, S_pad, seq, head, qt * 16 + g + 8, n * 4 + t, b0, b1);
+          s[n][0] *= a0; s[n][1] *= a1; s[n][2] *= b0; s[n][3] *= b1;
+        }
+      }
+    }
     // O = P V
     float o[8][4];
 #pragma unroll
@@ -563,6 +588,12 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
         const float mk0 = sMask[kb * 16 + n * 8 + 2 * t], mk1 = sMask[kb * 16 + n * 8 + 2 * t + 1];
+        if (p.drop_thr) {   // dP flows through the dropout mask of the forward pass
+          float a0, a1, b0, b1;
+          drop_pair(p, S_pad, seq, head, qt * 16 + g, kb * 8 + n * 4 + t, a0, a1);
+          drop_pair(p, S_pad, seq, head, qt * 16 + g + 8, kb * 8 + n * 4 + t, b0, b1);
+          dp[n][0] *= a0; dp[n][1] *= a1; dp[n][2] *= b0; dp[n][3] *= b1;
+        }
         ds[n][0] = ex2(s[n][0] * sl2 + mk0 - ls0) * (dp[n][0] - D0) * p.scale;
         ds[n][1] = ex2(s[n][1] * sl2 + mk1 - ls0) * (dp[n][1] - D0) * p.scale;
         ds[n][2] = ex2(s[n][2] * sl2 + mk0 - ls1) * (dp[n][2] - D1) * p.scale;
@@ -637,10 +668,20 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
         pt[n][1] = v1 ? ex2(st[n][1] * sl2 + mk0 - l1) : 0.f;
         pt[n][2] = v0 ? ex2(st[n][2] * sl2 + mk1 - l0) : 0.f;
         pt[n][3] = v1 ? ex2(st[n][3] * sl2 + mk1 - l1) : 0.f;
-        dst_[n][0] = pt[n][0] * (dpt[n][0] - D0) * p.scale;
-        dst_[n][1] = pt[n][1] * (dpt[n][1] - D1) * p.scale;
-        dst_[n][2] = pt[n][2] * (dpt[n][2] - D0) * p.scale;
-        dst_[n][3] = pt[n][3] * (dpt[n][3] - D1) * p.scale;
+        float mq[4] = {1.f, 1.f, 1.f, 1.f};   // mask(query, key) for the 4 fragment elements (key rows g / g+8)
+        if (p.drop_thr) {
+          const int j0 = kt * 16 + g, j1 = j0 + 8;
+          float lo, hi;
+          drop_pair(p, S_pad, seq, head, qc, j0 >> 1, lo, hi);     mq[0] = (j0 & 1) ? hi : lo;
+          drop_pair(p, S_pad, seq, head, qc + 1, j0 >> 1, lo, hi); mq[1] = (j0 & 1) ? hi : lo;
+          drop_pair(p, S_pad, seq, head, qc, j1 >> 1, lo, hi);     mq[2] = (j1 & 1) ? hi : lo;
+          drop_pair(p, S_pad, seq, head, qc + 1, j1 >> 1, lo, hi); mq[3] = (j1 & 1) ? hi : lo;
+        }
+        dst_[n][0] = pt[n][0] * (dpt[n][0] * mq[0] - D0) * p.scale;
+        dst_[n][1] = pt[n][1] * (dpt[n][1] * mq[1] - D1) * p.scale;
+        dst_[n][2] = pt[n][2] * (dpt[n][2] * mq[2] - D0) * p.scale;
+        dst_[n][3] = pt[n][3] * (dpt[n][3] * mq[3] - D1) * p.scale;
+        pt[n][0] *= mq[0]; pt[n][1] *= mq[1]; pt[n][2] *= mq[2]; pt[n][3] *= mq[3];   // dV uses the dropped probabilities
       }
       uint32_t pa[4] = {pack2<BF>(pt[0][0], pt[0][1]), pack2<BF>(pt[0][2], pt[0][3]), pack2<BF>(pt[1][0], pt[1][1]),
                         pack2<BF>(pt[1][2], pt[1][3])};
@@ -761,7 +802,12 @@ extern "C" int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const vo
 }
 
 static int fill_sattn(SAttnParams& p, const void* qkv, int64_t ld_qkv, const float* mask, int S, int nseq, int heads,
-                      int fmt, int seq_div, int stride, int64_t clip_rows, float scale) {
+                      int fmt, int seq_div, int stride, int64_t clip_rows, float scale, float drop_p,
+                      uint32_t drop_seed) {
+  ALPRO_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "alpro_seq_attn: dropout probability out of range");
+  p.drop_thr = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  p.drop_seed = drop_seed;
+  p.drop_scale = 1.0f / (1.0f - drop_p);
   ALPRO_REQUIRE(qkv && S > 0 && S <= 256 && nseq > 0 && heads > 0, "alpro_seq_attn: bad args (S=%d must be <= 256)", S);
   ALPRO_REQUIRE(seq_div >= 1 && stride >= 1 && (ld_qkv % 8) == 0, "alpro_seq_attn: bad layout");
   p.qkv = static_cast<const uint16_t*>(qkv); p.ld_qkv = ld_qkv; p.mask = mask; p.S = S; p.nseq = nseq; p.heads = heads;
@@ -771,9 +817,9 @@ static int fill_sattn(SAttnParams& p, const void* qkv, int64_t ld_qkv, const flo
 
 extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* mask, void* o, int64_t ld_o,
                                   void* cls_o, float* lse, int S, int nseq, int heads, int fmt, int seq_div, int stride,
-                                  int64_t clip_rows, float scale, void* stream) {
+                                  int64_t clip_rows, float scale, float drop_p, uint32_t drop_seed, void* stream) {
   SAttnParams p{};
-  int rc = fill_sattn(p, qkv, ld_qkv, mask, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale);
+  int rc = fill_sattn(p, qkv, ld_qkv, mask, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale, drop_p, drop_seed);
   if (rc) return rc;
   ALPRO_REQUIRE(o && (ld_o % 8) == 0, "alpro_seq_attn_fwd: bad output");
   p.o = static_cast<uint16_t*>(o); p.ld_o = ld_o; p.cls_o = static_cast<uint16_t*>(cls_o); p.lse = lse;
@@ -808,9 +854,9 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
                                   const void* cls_fwd, const float* cls_weight, const void* dout, int64_t ld_o,
                                   void* dqkv, float* dcls_qkv_scratch, int S, int nseq,
                                   int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
-                                  void* stream) {
+                                  float drop_p, uint32_t drop_seed, void* stream) {
   SAttnParams p{};
-  int rc = fill_sattn(p, qkv, ld_qkv, mask, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale);
+  int rc = fill_sattn(p, qkv, ld_qkv, mask, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale, drop_p, drop_seed);
   if (rc) return rc;
   ALPRO_REQUIRE(lse && dout && dqkv && o_fwd && (ld_o % 8) == 0, "alpro_seq_attn_bwd: bad args");
   ALPRO_REQUIRE(seq_div == 1 || cls_fwd, "alpro_seq_attn_bwd: shared-cls layout needs the per-sequence cls outputs");
@@ -843,5 +889,35 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
                                                                     seq_div, 3 * p.d, fmt);
     ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd(cls reduce)");
   }
+  return 0;
+}
+
+namespace alpro {
+namespace {
+__global__ void attn_drop_mask_kernel(float* __restrict__ out, int S, int S_pad, int nseq, int heads, uint32_t thr,
+                                      uint32_t seed, float scale) {
+  SAttnParams p{};
+  p.heads = heads; p.drop_thr = thr; p.drop_seed = seed; p.drop_scale = scale;
+  const long long total = static_cast<long long>(nseq) * heads * S * S;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % S);
+    const int q = static_cast<int>((i / S) % S);
+    const long long sh = i / (static_cast<long long>(S) * S);
+    float lo, hi;
+    drop_pair(p, S_pad, static_cast<int>(sh / heads), static_cast<int>(sh % heads), q, j >> 1, lo, hi);
+    out[i] = (j & 1) ? hi : lo;
+  }
+}
+}  // namespace
+}  // namespace alpro
+
+extern "C" int alpro_attn_dropout_mask(float* out, int S, int nseq, int heads, float drop_p, uint32_t drop_seed,
+                                       void* stream) {
+  ALPRO_REQUIRE(out && S > 0 && nseq > 0 && heads > 0 && drop_p > 0.f && drop_p < 1.f, "alpro_attn_dropout_mask: bad args");
+  const int S_pad = (S + 15) & ~15;
+  attn_drop_mask_kernel<<<num_sms() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, S, S_pad, nseq, heads, drop_threshold(drop_p), drop_seed, 1.0f / (1.0f - drop_p));
+  ALPRO_CHECK_LAUNCH("alpro_attn_dropout_mask");
   return 0;
 }

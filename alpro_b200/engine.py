@@ -29,9 +29,14 @@ class OperandCache:
     def __init__(self, dtype):
         self.dtype = dtype
         self._c = {}
+        self._epoch = 0
 
     def _key(self, ps):
-        return tuple((p.data_ptr(), p._version) for p in ps)
+        return tuple((p.data_ptr(), p._version, self._epoch) for p in ps)
+
+    def invalidate(self):
+        """Force a refresh of every operand copy (used after an out-of-band parameter update, e.g. FusedAdamW)."""
+        self._epoch += 1
 
     def get(self, name, p, shape2d=None):
         ent = self._c.get(name)
@@ -409,7 +414,7 @@ class BertEncoder:
                                G[e + "position_embeddings.weight"], G[e + "token_type_embeddings.weight"][0],
                                ctx["L"], h, 1.0 / S)
 
-    def forward(self, P, W, x32, x16, add_mask, nseq, S_len, mode, save, pdrop=0.0, seeds=None):
+    def forward(self, P, W, x32, x16, add_mask, nseq, S_len, mode, save, pdrop=0.0, seeds=None, pattn=0.0):
         """x32/x16: [nseq*S_len, h]; add_mask fp32 [nseq, S_len]. Returns (y32, y16, ctx).
         pdrop > 0: train-mode hidden dropout after both dense output layers (xbert.py:358, 436)."""
         dev = x32.device
@@ -427,7 +432,8 @@ class BertEncoder:
             ops.gemm16(x16, Wq, bias=bq, out16=qkv)
             cx = _empty((M, h), dt, dev)
             lse = _empty((nseq, heads, S_len), torch.float32, dev)
-            ops.seq_attn_fwd(qkv, add_mask, cx, None, lse, S_len, nseq, heads, 1, 1, S_len, scale)
+            aseed = next(seeds) if pattn > 0 else 0
+            ops.seq_attn_fwd(qkv, add_mask, cx, None, lse, S_len, nseq, heads, 1, 1, S_len, scale, pattn, aseed)
             z1 = _empty((M, h), torch.float32, dev)
             mo = self._mask((M, h), pdrop, seeds, dev) if pdrop > 0 else None
             mf = self._mask((M, h), pdrop, seeds, dev) if pdrop > 0 else None
@@ -453,7 +459,7 @@ class BertEncoder:
                               out16=y16, mean=st2[0], rstd=st2[1])
             if save:
                 ctx["layers"].append(dict(i=i, x16=x16, qkv=qkv, cx=cx, lse=lse, z1=z1, st1=st1, a16=a16, hdn=hdn,
-                                          pre=pre, z2=z2, st2=st2, mo=mo, mf=mf))
+                                          pre=pre, z2=z2, st2=st2, mo=mo, mf=mf, pattn=pattn, aseed=aseed))
             x32, x16 = y32, y16
         return x32, x16, ctx
 
@@ -499,7 +505,7 @@ class BertEncoder:
             wgrad(dz1_16, c["cx"], G[l + "attention.output.dense.weight"])
             dqkv = _empty((M, 3 * h), dt, dev)
             ops.seq_attn_bwd(c["qkv"], ctx["mask"], c["lse"], c["cx"], None, dcx, dqkv, None, S_len, nseq, heads, 1, 1,
-                             S_len, scale)
+                             S_len, scale, drop_p=c["pattn"], drop_seed=c["aseed"])
             Wq, _ = self._qkv(P, W, l)
             dx32 = da32  # reuse
             ops.gemm16(dqkv, Wq, b_layout=MNMAJOR, resid=dz1, out32=dx32)
@@ -582,7 +588,7 @@ class AlproEngine:
     def forward(self, P, batch, need_grad=True, training=False):
         """Returns (outputs, ctx). outputs mirrors the reference dict (alpro_models.py:172-183, 793-798).
         training=True applies the reference's train-mode regularisers: BERT hidden dropout (xbert.py:178,358,436) and
-        TimeSformer stochastic depth (vit.py:157,181,212). Attention-probability dropout (xbert.py:331) is not applied."""
+        attention-probability dropout (xbert.py:331), TimeSformer stochastic depth (vit.py:157,181,212)."""
         kind = self.kind
         dev = batch["visual_inputs"].device
         cfg, h, d = self.cfg, self.cfg["hidden_size"], self.vis["d"]
@@ -593,7 +599,8 @@ class AlproEngine:
         B = frames.shape[0]
         pdrop = float(cfg.get("hidden_dropout_prob", 0.0)) if training else 0.0
         dpr = float(self.vis.get("drop_path_rate", 0.0)) if training else 0.0
-        seeds = self._seed_stream() if pdrop > 0 else None
+        pattn = float(cfg.get("attention_probs_dropout_prob", 0.0)) if training else 0.0
+        seeds = self._seed_stream() if (pdrop > 0 or pattn > 0) else None
         ve, vctx = self.visual.forward(P, self.W, frames, save, drop_path_rate=dpr)     # [B, Nv, d]
         Nv = ve.shape[1]
         ids, mask = batch["text_input_ids"], batch["text_input_mask"]
@@ -609,7 +616,7 @@ class AlproEngine:
         mask_all = mask_all.contiguous()
         x32, x16, ectx = self.bert.embed(P, ids_all, save, pdrop, seeds)
         te, _, tctx = self.bert.forward(P, self.W, x32, x16, self._text_mask_add(mask_all), nt, L, "text", save, pdrop,
-                                        seeds)
+                                        seeds, pattn)
         te = te.view(nt, L, h)
 
         # ---- VTC (alpro_models.py:103-128, 750-779)
@@ -653,7 +660,7 @@ class AlproEngine:
         f16 = _empty((S_all * R, h), self.dtype, dev)
         fmask = _empty((S_all, R), torch.float32, dev)
         ops.fusion_gather_fwd(te, ve, mask_all, ti, vi, f32, f16, fmask, S_all, L, Nv, h)
-        fo, _, fctx = self.bert.forward(P, self.W, f32, f16, fmask, S_all, R, "fusion", save, pdrop, seeds)
+        fo, _, fctx = self.bert.forward(P, self.W, f32, f16, fmask, S_all, R, "fusion", save, pdrop, seeds, pattn)
 
         # ---- VTM head (alpro_models.py:334-339)
         itm_scores = _empty((3 * B, 2), torch.float32, dev)

@@ -217,18 +217,24 @@ def temporal_attn_bwd(qkv, dout, dqkv, B, N, T, heads, scale):
                                      T, heads, _fmt(qkv), scale, _s()), "alpro_temporal_attn_bwd")
 
 
-def seq_attn_fwd(qkv, mask, o, cls_o, lse, S, nseq, heads, seq_div, stride, clip_rows, scale):
+def seq_attn_fwd(qkv, mask, o, cls_o, lse, S, nseq, heads, seq_div, stride, clip_rows, scale, drop_p=0.0, drop_seed=0):
     check(_L.alpro_seq_attn_fwd(_p(qkv), qkv.stride(0), _p(mask), _p(o), o.stride(0), _p(cls_o), _p(lse), S, nseq,
-                                heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()), "alpro_seq_attn_fwd")
+                                heads, _fmt(qkv), seq_div, stride, clip_rows, scale, drop_p, drop_seed & 0xffffffff,
+                                _s()), "alpro_seq_attn_fwd")
+
+
+def attn_dropout_mask(out, S, nseq, heads, drop_p, drop_seed):
+    check(_L.alpro_attn_dropout_mask(_p(out), S, nseq, heads, drop_p, drop_seed & 0xffffffff, _s()),
+          "alpro_attn_dropout_mask")
 
 
 def seq_attn_bwd(qkv, mask, lse, o_fwd, cls_fwd, dout, dqkv, scratch, S, nseq, heads, seq_div, stride, clip_rows, scale,
-                 cls_weight=None):
+                 cls_weight=None, drop_p=0.0, drop_seed=0):
     assert o_fwd.stride(0) == dout.stride(0)
     check(_L.alpro_seq_attn_bwd(_p(qkv), qkv.stride(0), _p(mask), _p(lse), _p(o_fwd), _p(cls_fwd), _p(cls_weight), _p(dout),
                                 dout.stride(0), _p(dqkv),
-                                _p(scratch), S, nseq, heads, _fmt(qkv), seq_div, stride, clip_rows, scale, _s()),
-          "alpro_seq_attn_bwd")
+                                _p(scratch), S, nseq, heads, _fmt(qkv), seq_div, stride, clip_rows, scale, drop_p,
+                                drop_seed & 0xffffffff, _s()), "alpro_seq_attn_bwd")
 
 
 def small_linear_fwd(x, ldx, W, b, y, M, N, K, alpha=1.0, alpha_dev=None, alpha_mode=0, relu=False, ldw=None, ldy=None):
@@ -330,3 +336,12 @@ def gelu_grad_mul(dy32, pre16, out16):
 def pseudo_labels(sim, soft, ignore):
     R, C = sim.shape
     check(_L.alpro_pseudo_labels(_p(sim), R, C, _p(soft), _p(ignore), _s()), "alpro_pseudo_labels")
+
+
+def sumsq(x, out):
+    check(_L.alpro_sumsq(_p(x), x.numel(), _p(out), _s()), "alpro_sumsq")
+
+
+def adamw_step(p, g, m, v, beta1, beta2, eps, step_size, lr_wd, gnorm_sq, max_norm):
+    check(_L.alpro_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), beta1, beta2, eps, step_size, lr_wd,
+                              _p(gnorm_sq), max_norm, _s()), "alpro_adamw_step")

@@ -1,0 +1,64 @@
+"""Fused AdamW + global-norm clipping on the flat gradient buffer.
+
+Replaces `clip_grad_norm_(...)` + `AdamW.step()` of the reference trainers (run_video_retrieval.py:473-490,
+src/optimization/adamw.py:40-103) with two kernel launches over flat fp32 buffers. The parameters of the model are
+re-pointed to views of one flat buffer laid out exactly like the engine's GradStore, so `grad`, `exp_avg`, `exp_avg_sq`
+and the parameters are element-aligned."""
+import math
+
+import torch
+
+from . import ops
+from .engine import GradStore, bert_grad_groups
+
+
+class FusedAdamW:
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True,
+                 max_grad_norm=-1.0):
+        self.model = model
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.correct_bias, self.max_grad_norm = correct_bias, max_grad_norm
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and not n.startswith("prompter.")]
+        dev = named[0][1].device
+        layout = GradStore(named, dev, bert_grad_groups("text_encoder.", model.engine.cfg))
+        self.offsets = layout.offsets
+        self.numel = layout.flat.numel()
+        assert self.numel % 4 == 0
+        self.flat = layout.flat          # reuse the zero-filled buffer as parameter storage
+        with torch.no_grad():
+            for n, p in named:
+                o, cnt, shape = self.offsets[n]
+                view = self.flat[o:o + cnt].view(shape)
+                view.copy_(p.data)
+                p.data = view
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_count = 0
+
+    def step(self):
+        G = self.model.engine.last_grads
+        if G is None:
+            raise RuntimeError("FusedAdamW.step(): run loss.backward() first")
+        assert G.offsets == self.offsets, "gradient layout changed"
+        self.step_count += 1
+        b1, b2 = self.betas
+        step_size = self.lr
+        if self.correct_bias:
+            step_size = step_size * math.sqrt(1.0 - b2 ** self.step_count) / (1.0 - b1 ** self.step_count)
+        gn = None
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            self.gnorm_sq.zero_()
+            ops.sumsq(G.flat, self.gnorm_sq)
+            gn = self.gnorm_sq
+        ops.adamw_step(self.flat, G.flat, self.exp_avg, self.exp_avg_sq, b1, b2, self.eps, step_size,
+                       self.lr * self.wd, gn, self.max_grad_norm if gn is not None else -1.0)
+        self.model.engine.W.invalidate()     # 16-bit operand copies are stale now
+
+    def grad_norm(self):
+        """sqrt of the last computed squared gradient norm (device tensor; no sync)."""
+        return self.gnorm_sq.sqrt()
+
+    def zero_grad(self):
+        for p in self.model.parameters():
+            p.grad = None

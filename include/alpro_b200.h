@@ -152,15 +152,19 @@ int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const void* dout, i
  * xbert.py:263-346). Token j of sequence s lives at row (s/seq_div)*clip_rows + (j==0 ? 0 : 1 + s%seq_div + (j-1)*stride):
  *   BERT: seq_div=1, stride=1, clip_rows=S.   TimeSformer spatial: seq_div=T, stride=T, clip_rows=1+N*T, S=1+N.
  * With seq_div>1 the per-frame cls outputs go to cls_o [nseq,d] (mean taken by alpro_cls_mean_fwd). lse: [nseq,heads,S]. */
+/* drop_p > 0: train-mode dropout of the attention probabilities (xbert.py:331) from the stateless hash (drop_seed). */
 int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* mask, void* o, int64_t ld_o, void* cls_o, float* lse,
                        int S, int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
-                       void* stream);
+                       float drop_p, uint32_t drop_seed, void* stream);
 /* backward: o_fwd = the forward output rows, cls_fwd = the forward per-sequence token-0 outputs (cls_o, seq_div > 1 only),
  * cls_weight (optional [nseq]) = weight of each frame's cls output in the group's cls row (default 1/seq_div) */
 int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const float* lse, const void* o_fwd,
                        const void* cls_fwd, const float* cls_weight, const void* dout, int64_t ld_o, void* dqkv,
                        float* dcls_qkv_scratch, int S,
-                       int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale, void* stream);
+                       int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale, float drop_p,
+                       uint32_t drop_seed, void* stream);
+/* test utility: materialises the mask/keep factors [nseq, heads, S, S] the two functions above apply for (drop_p, seed) */
+int alpro_attn_dropout_mask(float* out, int S, int nseq, int heads, float drop_p, uint32_t drop_seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Task-head kernels, fp32 (alpro_b200/csrc/heads.cu)
@@ -203,6 +207,16 @@ int alpro_gelu_grad_mul(const float* dy, const void* dact, int dact_fmt, void* o
 int alpro_pseudo_labels(const float* sim, int R, int C, float* soft, uint8_t* ignore, void* stream);
 /* hard-negative sampling weights: softmax of the local sim block with -inf diagonal (alpro_models.py:288-299) */
 int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, float* w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused optimizer step over flat buffers (alpro_b200/csrc/optim.cu)
+ */
+/* *out += sum_i x[i]^2   (global gradient norm for clip_grad_norm_, run_video_retrieval.py:473-476) */
+int alpro_sumsq(const float* x, int64_t n, float* out, void* stream);
+/* AdamW of src/optimization/adamw.py:40-103 on flat p/g/m/v (n % 4 == 0); g is scaled by min(1, max_norm/(sqrt(*gnorm_sq)+1e-6))
+ * when max_norm > 0; step_size = lr*sqrt(1-b2^t)/(1-b1^t) (or lr without bias correction); lr_wd = lr*weight_decay */
+int alpro_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                     float step_size, float lr_wd, const float* gnorm_sq, float max_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -140,7 +140,10 @@ def bert_layer(sd, l, x, ext_mask, heads, eps, drop=None):
             .view(Bp, S, heads, dh).transpose(1, 2)
     q, k, v = proj("query"), proj("key"), proj("value")
     scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh) + ext_mask           # xbert.py:317-320
-    ctx = (torch.softmax(scores, dim=-1) @ v).transpose(1, 2).reshape(Bp, S, h)
+    probs = torch.softmax(scores, dim=-1)
+    if drop is not None and len(drop) > 2 and drop[2] is not None:
+        probs = probs * drop[2]                                             # attention_probs dropout, xbert.py:331
+    ctx = (probs @ v).transpose(1, 2).reshape(Bp, S, h)
     a = F.linear(ctx, sd[l + "attention.output.dense.weight"], sd[l + "attention.output.dense.bias"])
     if drop is not None:
         a = a * drop[0].reshape(a.shape)                                    # BertSelfOutput.dropout, xbert.py:358

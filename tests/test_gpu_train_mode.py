@@ -104,11 +104,28 @@ def _collect_train_masks(model, cfg):
     h = cfg["bert"]["hidden_size"]
     L, R = ctx["L"], ctx["R"]
     tr["emb"] = ctx["ectx"]["mask"].float().cpu().view(-1, L, h)[:B]
-    tr["text"] = {c["i"]: (c["mo"].float().cpu().view(-1, L, h)[:B], c["mf"].float().cpu().view(-1, L, h)[:B])
-                  for c in ctx["tctx"]["layers"]}
-    fus = {c["i"]: (c["mo"].float().cpu().view(-1, R, h), c["mf"].float().cpu().view(-1, R, h)) for c in ctx["fctx"]["layers"]}
-    tr["pos"] = {i: (a[:B], b[:B]) for i, (a, b) in fus.items()}
-    tr["neg"] = {i: (a[B:3 * B], b[B:3 * B]) for i, (a, b) in fus.items()}
+    from alpro_b200 import ops
+    heads = cfg["bert"]["num_attention_heads"]
+
+    def amask(c, S, nseq):
+        if not c["pattn"]:
+            return None
+        m = torch.empty(nseq, heads, S, S, device="cuda")
+        ops.attn_dropout_mask(m, S, nseq, heads, c["pattn"], c["aseed"])
+        return m.cpu()
+
+    nt, S_all = ctx["nt"], ctx["S_all"]
+    tr["text"] = {}
+    for c in ctx["tctx"]["layers"]:
+        am = amask(c, L, nt)
+        tr["text"][c["i"]] = (c["mo"].float().cpu().view(-1, L, h)[:B], c["mf"].float().cpu().view(-1, L, h)[:B],
+                              None if am is None else am[:B])
+    tr["pos"], tr["neg"] = {}, {}
+    for c in ctx["fctx"]["layers"]:
+        a, b = c["mo"].float().cpu().view(-1, R, h), c["mf"].float().cpu().view(-1, R, h)
+        am = amask(c, R, S_all)
+        tr["pos"][c["i"]] = (a[:B], b[:B], None if am is None else am[:B])
+        tr["neg"][c["i"]] = (a[B:3 * B], b[B:3 * B], None if am is None else am[B:3 * B])
     return tr
 
 
@@ -123,6 +140,8 @@ def test_train_mode_step_matches_oracle_with_injected_masks():
     (out["itc_loss"] + out["itm_loss"]).backward()
     assert any(d is not None for d in tr["drop_path"])          # stochastic depth really was active
     assert float((tr["emb"] == 0).float().mean()) > 0.05         # and so was dropout
+    am = next(iter(tr["pos"].values()))[2]
+    assert am is not None and abs(float((am == 0).float().mean()) - 0.1) < 0.02   # attention-prob dropout too
     # eval-mode result must differ (the regularisers do something) ...
     model.eval()
     out_eval = model(to_cuda(batch))
