@@ -267,7 +267,7 @@ def run_ours(args):
                      "traffic": None},
     }
     if world == 1 and not args.no_cpu_baseline:
-        res["cpu_baseline"] = cpu_baseline(kind, steps=1)
+        res["cpu_baseline"] = cpu_baseline(kind)
     print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -289,7 +289,7 @@ def usable_cores(cap=32):
     return max(1, min(n, cap))
 
 
-def cpu_baseline(kind, steps=1, B=1):
+def cpu_baseline(kind, steps=2, B=4):
     """The oracle (CPU restatement of the reference path, pinned to the reference's golden vectors) on the host cores.
     Bounded sample: B clips of the same workload (8x224^2, L=40, full-size model), fwd+bwd."""
     from alpro_b200 import synth
