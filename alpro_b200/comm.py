@@ -36,14 +36,78 @@ class TorchDistComm:
         return out
 
 
-def attach(model, group=None):
-    """Make `model` exchange VTC features across the ranks of `group` (call after dist.init_process_group)."""
+class BucketedAllReduce:
+    """Gradient averaging overlapped with the backward pass.
+
+    The backward writes all gradients into one flat buffer whose layout follows completion order (GradStore.regions);
+    the engine calls `ready(G, end)` whenever the prefix [0, end) is final. Ready slices are all-reduced (AVG) on a side
+    stream in buckets of at least `min_bucket` elements while the remaining TimeSformer blocks are still running their
+    backward; `finish()` (called by allreduce_gradients) flushes the tail and joins the streams. Replaces the blocking
+    `optimizer.synchronize()` of hvd.DistributedOptimizer (run_video_retrieval.py:444)."""
+
+    def __init__(self, group=None, min_bucket=32 * 1024 * 1024):
+        self.group = group
+        self.min_bucket = min_bucket
+        self.world = dist.get_world_size(group)
+        self._gloo = dist.get_backend(group) == "gloo"
+        self.side = torch.cuda.Stream() if torch.cuda.is_available() and not self._gloo else None
+        self._done = 0
+        self._G = None
+        self.bytes = 0
+
+    def _reduce(self, flat, lo, hi):
+        if hi <= lo:
+            return
+        sl = flat[lo:hi]
+        self.bytes += (hi - lo) * 4
+        if self._gloo:
+            dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group)
+            sl.div_(self.world)
+            return
+        ev = torch.cuda.Event()
+        ev.record()                                   # gradients of [lo, hi) are complete on the compute stream here
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group)
+
+    def ready(self, G, end):
+        if self._G is not G:                          # new backward pass
+            self._G, self._done, self.bytes = G, 0, 0
+        final = end >= G.flat.numel()
+        if end - self._done >= self.min_bucket or final:
+            self._reduce(G.flat, self._done, end)
+            self._done = end
+
+    def finish(self):
+        G = self._G
+        if G is None:
+            raise RuntimeError("no gradients to reduce: run loss.backward() first")
+        if self._done < G.flat.numel():
+            self._reduce(G.flat, self._done, G.flat.numel())
+            self._done = G.flat.numel()
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self._G = None
+        return self.bytes
+
+
+def attach(model, group=None, overlap=True):
+    """Make `model` exchange VTC features across the ranks of `group` and (overlap=True) average its gradients while
+    the backward pass is still running (call after dist.init_process_group)."""
     model.engine.comm = TorchDistComm(group)
+    if overlap:
+        model._grad_reducer = BucketedAllReduce(group)
+        model.engine.grad_ready_hook = model._grad_reducer.ready
     return model
 
 
 def allreduce_gradients(model, group=None):
-    """Average all parameter gradients across ranks with one collective over the flat gradient buffer."""
+    """Average all parameter gradients across ranks. With comm.attach(model, overlap=True) most of the buffer has already
+    been reduced on the side stream during backward and only the tail + stream join happen here; otherwise one collective
+    over the flat gradient buffer."""
+    red = getattr(model, "_grad_reducer", None)
+    if red is not None and red._G is not None:
+        return red.finish()
     flat = getattr(model.engine, "last_grads", None)
     if flat is None:
         raise RuntimeError("no gradients to reduce: run loss.backward() first")

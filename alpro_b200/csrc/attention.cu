@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
 // grid (heads, nseq), 128 threads. smem: Q, K, V, dO tiles + lse2[S_pad] (base-2 log-sum-exp) + D[S_pad] + mask.
 // Phase A: each warp owns 16-query tiles -> dQ.   Phase B: each warp owns 16-key tiles -> dK, dV (recomputing S^T).
 template <bool BF>
-__global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
+__global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) {
   extern __shared__ __align__(128) uint8_t sm[];
   const int head = blockIdx.x, seq = blockIdx.y;
   const int S_pad = (p.S + 15) & ~15;
@@ -528,11 +528,11 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
 
   // ---------------- D_i = rowsum(dO_i * O_i): O from global (coalesced 128-byte rows, 8 rows in flight per warp),
   // dO from the staged tile
-  for (int r0 = warp; r0 < S_pad; r0 += 32) {
+  for (int r0 = warp; r0 < S_pad; r0 += 64) {
     uint32_t wo[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int r = r0 + 4 * u;
+      const int r = r0 + 8 * u;
       wo[u] = 0u;
       if (r < p.S) {
         const uint16_t* orow = (r == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int r = r0 + 4 * u;
+      const int r = r0 + 8 * u;
       if (r < S_pad) {   // warp-uniform
         const int ch = lane >> 2;   // 16-byte chunk of the dO row holding columns 2*lane, 2*lane+1
         const uint32_t wg = *reinterpret_cast<const uint32_t*>(sG + r * 128 + ((ch ^ (r & 7)) << 4) + ((lane & 3) << 2));
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
   __syncthreads();
 
   // ---------------- phase A: dQ (warp per 16-query tile)
-  for (int qt = warp; qt < nkb; qt += 4) {
+  for (int qt = warp; qt < nkb; qt += 8) {
     uint32_t qa[4][4], ga[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(128) sattn_bwd_kernel(const SAttnParams p) {
   }
 
   // ---------------- phase B: dK, dV (warp per 16-key tile); S^T = K Q^T, dP^T = V dO^T
-  for (int kt = warp; kt < nkb; kt += 4) {
+  for (int kt = warp; kt < nkb; kt += 8) {
     uint32_t ka[4][4], va[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -874,11 +874,11 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   if (fmt == 1) {
     rc = set_smem(sattn_bwd_kernel<true>, smem);
     if (rc) return rc;
-    sattn_bwd_kernel<true><<<grid, 128, smem, st>>>(p);
+    sattn_bwd_kernel<true><<<grid, 256, smem, st>>>(p);
   } else {
     rc = set_smem(sattn_bwd_kernel<false>, smem);
     if (rc) return rc;
-    sattn_bwd_kernel<false><<<grid, 128, smem, st>>>(p);
+    sattn_bwd_kernel<false><<<grid, 256, smem, st>>>(p);
   }
   ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd");
   if (seq_div > 1) {

@@ -82,17 +82,47 @@ class GradStore:
                 order.extend(names)
                 seen.update(names)
                 self.groups[gname] = names
-        order.extend(n for n in shapes if n not in seen)
+        # Region order = the order in which the backward pass FINISHES gradients, so that a data-parallel all-reduce of
+        # one contiguous slice can start while later regions are still being computed (comm.BucketedAllReduce):
+        #   region 0: everything outside the visual encoder (heads, fusion/text BERT, embeddings)
+        #   region 1+k: visual block (depth-1-k) [+ the final norm for k = 0]; last region: patch/pos/time/cls embeddings
+        rest = [n for n in shapes if n not in seen]
+        vis = [n for n in rest if n.startswith("visual_encoder.")]
+        nonvis = [n for n in rest if not n.startswith("visual_encoder.")]
+
+        def vis_key(n):
+            if ".blocks." in n:
+                return (1, -int(n.split(".blocks.")[1].split(".")[0]))
+            if ".model.norm." in n or ".model.head." in n:
+                return (0, 0)
+            return (2, 0)
+        vis.sort(key=vis_key)                      # stable: keeps the module order inside a block
+        order.extend(nonvis)
+        n_nonvis = len(order)
+        order.extend(vis)
         total = 0
         self.offsets = {}
-        for n in order:
+        self.regions = []                          # [(lo, hi, tag)] element ranges in `flat`, in completion order
+        cur_tag, cur_lo = ("nonvis",), 0
+        for idx, n in enumerate(order):
+            tag = ("nonvis",) if idx < n_nonvis else vis_key(n)
+            if tag != cur_tag:
+                self.regions.append((cur_lo, total, cur_tag))
+                cur_tag, cur_lo = tag, total
             numel = 1
             for v in shapes[n]:
                 numel *= v
             assert numel % 4 == 0 or n not in seen, "grouped parameters must keep 16-byte alignment"
             self.offsets[n] = (total, numel, shapes[n])
             total += numel if n in seen else (numel + 3) // 4 * 4
+        self.regions.append((cur_lo, total, cur_tag))
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+
+    def region_end(self, tag):
+        for lo, hi, t in self.regions:
+            if t == tag:
+                return hi
+        return None
 
     def __getitem__(self, n):
         o, numel, shape = self.offsets[n]
@@ -267,8 +297,9 @@ class VisualEncoder:
             ctx.update(x_final=x, st_f=st_f)
         return ve, ctx
 
-    def backward(self, P, W, ctx, d_ve, G, S):
-        """d_ve: fp32 [B,1+N,d] gradient of video_embeds (already multiplied by the loss scale S). Fills G[...]."""
+    def backward(self, P, W, ctx, d_ve, G, S, hook=None):
+        """d_ve: fp32 [B,1+N,d] gradient of video_embeds (already multiplied by the loss scale S). Fills G[...].
+        hook(G, end): called whenever the flat gradient prefix [0, end) has become final (after each block)."""
         B, T, N = ctx["B"], ctx["T"], ctx["N"]
         d, heads, dt = self.d, self.heads, self.dtype
         dev = d_ve.device
@@ -343,6 +374,10 @@ class VisualEncoder:
                               param_scale=inv, colsum=nxt, colsum_zero_period=0 if i > 0 else Sc,
                               dx16_row_scale=dp_prev["rs_m"] if dp_prev else None)
             ctx["blocks"][i] = None  # release saved activations
+            if hook is not None and i > 0:
+                # every gradient of block i is final here (its mlp.fc2.bias came from the LayerNorm backward that ran
+                # before this block's GEMMs); block i-1's region is still open
+                hook(G, G.region_end((1, -i)))
         # ---- embeddings (vit.py:324-361) and patch projection
         pos_idx, tim_idx = ctx["pos_idx"], ctx["tim_idx"]
         gpos, gtim = G[p + "pos_embed"][0], G[p + "time_embed"][0]
@@ -559,6 +594,7 @@ class AlproEngine:
         self.last_grads = None
         self.base_seed = 0x5DEECE66
         self._step = 0
+        self.grad_ready_hook = None
 
     # ------------------------------------------------------------------------------------------------ features
     def _proj_norm(self, P, x, ldx, wname, rows):
@@ -824,8 +860,13 @@ class AlproEngine:
         # ---- encoders
         dx_text = self.bert.backward(P, self.W, ctx["tctx"], dte.view(nt * L, h), G, S)
         self.bert.embed_backward(P, ctx["ectx"], dx_text, G, S)
-        self.visual.backward(P, self.W, ctx["vctx"], dve, G, S)
         self.last_grads = G
+        hook = self.grad_ready_hook                    # data-parallel overlap: called with the flat prefix that is final
+        if hook is not None:
+            hook(G, G.region_end(("nonvis",)))
+        self.visual.backward(P, self.W, ctx["vctx"], dve, G, S, hook)
+        if hook is not None:
+            hook(G, G.flat.numel())
         return G
 
     def _mlm_backward(self, P, ctx, G, gptr, dfo):

@@ -47,6 +47,21 @@ def _worker(rank, world, port, q):
     rs = comm.reduce_scatter_sum(g.clone())
     full = torch.arange(3 * world * 4, dtype=torch.float32).view(3 * world, 4) * sum(r + 1 for r in range(world))
     assert torch.equal(rs, full[3 * rank:3 * rank + 3])
+    # 1b) bucketed gradient averaging: prefixes become final in several steps, result = mean over ranks
+    from alpro_b200.comm import BucketedAllReduce
+
+    class FakeG:
+        pass
+    G = FakeG()
+    G.flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    red = BucketedAllReduce(min_bucket=300)
+    for end in (100, 250, 420, 700, 990):
+        red.ready(G, end)
+    assert red._done in (420, 990) or red._done >= 300
+    nbytes = red.finish()
+    assert nbytes == 4000
+    want = torch.arange(1000, dtype=torch.float32) * (sum(r + 1 for r in range(world)) / world)
+    assert torch.allclose(G.flat, want)
     # 2) VTC through the oracle with a differentiable gather
     b, d = 4, 32
     gen = torch.Generator().manual_seed(5)
