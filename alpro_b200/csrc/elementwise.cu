@@ -360,6 +360,40 @@ __global__ void patchify_kernel(const float* __restrict__ frames, uint16_t* __re
   }
 }
 
+// Same gather from RAW uint8 frames [B,T,3,H,W] with the input normalisation fused in:
+// x = (u8 / 255 - mean[c]) / std[c]   (ImageNorm, src/datasets/data_utils.py:437-457). 4x fewer H2D / HBM bytes.
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ frames, uint16_t* __restrict__ out, int fmt, int B,
+                                   int T, int H, int W, int P, float s0, float s1, float s2, float o0, float o1,
+                                   float o2) {
+  const int gw = W / P, gh = H / P;
+  const int N = gw * gh;
+  const int Kd = 3 * P * P;
+  const int k4 = Kd >> 2;
+  const long long rows = static_cast<long long>(B) * (1 + N * T);
+  const long long total = rows * k4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / k4;
+    const int k = static_cast<int>(i - row * k4) * 4;
+    const int b = static_cast<int>(row / (1 + N * T));
+    const int j = static_cast<int>(row - static_cast<long long>(b) * (1 + N * T));
+    uint2 w = make_uint2(0u, 0u);
+    if (j > 0) {
+      const int n = (j - 1) / T, t = (j - 1) - n * T;
+      const int py = n / gw, px = n - py * gw;
+      const int c = k / (P * P);
+      const int rem = k - c * P * P;
+      const int ky = rem / P, kx = rem - ky * P;
+      const uchar4 v = *reinterpret_cast<const uchar4*>(
+          frames + (((static_cast<long long>(b) * T + t) * 3 + c) * H + (py * P + ky)) * W + px * P + kx);
+      const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), of = c == 0 ? o0 : (c == 1 ? o1 : o2);
+      w.x = pack2_16(fmaf(v.x, sc, of), fmaf(v.y, sc, of), fmt);
+      w.y = pack2_16(fmaf(v.z, sc, of), fmaf(v.w, sc, of), fmt);
+    }
+    *reinterpret_cast<uint2*>(out + row * Kd + k) = w;
+  }
+}
+
 // x[b,0] = cls + pos[0];  x[b,1+n*T+t] = proj[b,1+n*T+t] + pos[1+n] + time[t]      (vit.py:324-361)
 __global__ void vit_embed_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ cls,
                                      const float* __restrict__ pos, const float* __restrict__ tim,
@@ -757,5 +791,21 @@ extern "C" int alpro_dropout_mask(void* out16, int fmt, int64_t n, float p, uint
   dropout_mask_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<uint16_t*>(out16), fmt, n, drop_threshold(p), 1.0f / (1.0f - p), seed);
   ALPRO_CHECK_LAUNCH("alpro_dropout_mask");
+  return 0;
+}
+
+extern "C" int alpro_patchify_u8(const uint8_t* frames, void* out16, int fmt, int B, int T, int H, int W, int P,
+                                 const float* mean3, const float* std3, void* stream) {
+  ALPRO_REQUIRE(frames && out16 && mean3 && std3 && B > 0 && T > 0, "alpro_patchify_u8: bad args (mean3/std3 are HOST pointers)");
+  ALPRO_REQUIRE(P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "alpro_patchify_u8: P=%d H=%d W=%d unsupported", P, H, W);
+  float sc[3], of[3];
+  for (int c = 0; c < 3; ++c) {
+    sc[c] = 1.0f / (255.0f * std3[c]);
+    of[c] = -mean3[c] / std3[c];
+  }
+  const long long total = static_cast<long long>(B) * (1 + (H / P) * (W / P) * T) * (3 * P * P / 4);
+  patchify_u8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, static_cast<uint16_t*>(out16), fmt, B, T, H, W, P, sc[0], sc[1], sc[2], of[0], of[1], of[2]);
+  ALPRO_CHECK_LAUNCH("alpro_patchify_u8");
   return 0;
 }

@@ -36,6 +36,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ v, long long n, float beta1, float beta2, float eps, float step_size,
                              float lr_wd, const float* __restrict__ gnorm_sq, float max_norm) {
   float clip = 1.f;
+  if (gnorm_sq && !isfinite(*gnorm_sq)) return;   // fp16 gradient overflow: skip this update (dynamic loss scaling)
   if (max_norm > 0.f && gnorm_sq) {
     const float c = max_norm / (sqrtf(*gnorm_sq) + 1e-6f);
     clip = c < 1.f ? c : 1.f;

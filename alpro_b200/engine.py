@@ -159,6 +159,9 @@ class VisualEncoder:
         self.d, self.depth, self.heads = vis["d"], vis["depth"], vis["heads"]
         self.patch = vis["patch"]
         self.dtype = dtype
+        # ImageNorm constants for uint8 inputs (config img_pixel_mean/std, config_release/msrvtt_ret.json:19-20)
+        self.img_mean = vis.get("img_mean", (0.48145466, 0.4578275, 0.40821073))
+        self.img_std = vis.get("img_std", (0.26862954, 0.26130258, 0.27577711))
         assert self.d == self.heads * 64, "kernels assume head_dim 64"
 
     # ---- parameter helpers
@@ -216,7 +219,10 @@ class VisualEncoder:
 
         frames = frames.contiguous()
         patches = _empty((M, 3 * self.patch * self.patch), dt, dev)
-        ops.patchify(frames, patches, self.patch)
+        if frames.dtype == torch.uint8:   # raw frames: ImageNorm fused into the patch gather
+            ops.patchify_u8(frames, patches, self.patch, self.img_mean, self.img_std)
+        else:
+            ops.patchify(frames, patches, self.patch)
         Wpe = W.get(p + "patch_embed.proj.weight", P[p + "patch_embed.proj.weight"], (d, 3 * self.patch ** 2))
         proj = _empty((M, d), torch.float32, dev)
         ops.gemm16(patches, Wpe, bias=P[p + "patch_embed.proj.bias"].detach(), out32=proj)

@@ -161,6 +161,15 @@ def patchify(frames, out16, P):
     check(_L.alpro_patchify(_p(frames), _p(out16), _fmt(out16), B, T, H, W, P, _s()), "alpro_patchify")
 
 
+def patchify_u8(frames, out16, P, mean, std):
+    B, T, C, H, W = frames.shape
+    assert C == 3 and frames.is_contiguous() and frames.dtype == torch.uint8
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+    check(_L.alpro_patchify_u8(_p(frames), _p(out16), _fmt(out16), B, T, H, W, P, ctypes.cast(m, ctypes.c_void_p),
+                               ctypes.cast(sd, ctypes.c_void_p), _s()), "alpro_patchify_u8")
+
+
 def vit_embed_fwd(proj, cls, pos, tim, x, B, N, T, d):
     check(_L.alpro_vit_embed_fwd(_p(proj), _p(cls), _p(pos), _p(tim), _p(x), B, N, T, d, _s()), "alpro_vit_embed_fwd")
 

@@ -46,14 +46,28 @@ class FusedAdamW:
         step_size = self.lr
         if self.correct_bias:
             step_size = step_size * math.sqrt(1.0 - b2 ** self.step_count) / (1.0 - b1 ** self.step_count)
-        gn = None
-        if self.max_grad_norm is not None and self.max_grad_norm > 0:
-            self.gnorm_sq.zero_()
-            ops.sumsq(G.flat, self.gnorm_sq)
-            gn = self.gnorm_sq
+        # the squared gradient norm is always computed: it drives clipping and makes the kernel skip the update when the
+        # fp16 backward overflowed (non-finite norm)
+        self.gnorm_sq.zero_()
+        ops.sumsq(G.flat, self.gnorm_sq)
+        clip = self.max_grad_norm if (self.max_grad_norm is not None and self.max_grad_norm > 0) else -1.0
         ops.adamw_step(self.flat, G.flat, self.exp_avg, self.exp_avg_sq, b1, b2, self.eps, step_size,
-                       self.lr * self.wd, gn, self.max_grad_norm if gn is not None else -1.0)
+                       self.lr * self.wd, self.gnorm_sq, clip)
         self.model.engine.W.invalidate()     # 16-bit operand copies are stale now
+
+    def update_loss_scale(self, growth_interval=1000):
+        """Dynamic loss scaling for the fp16 backward (host sync: call every few steps, not every step). Halves the
+        engine's scale after an overflowed step (which the kernel skipped), doubles it after `growth_interval` good ones."""
+        eng = self.model.engine
+        if not bool(torch.isfinite(self.gnorm_sq).item()):
+            eng.S = max(eng.S * 0.5, 1.0)
+            self._good = 0
+        else:
+            self._good = getattr(self, "_good", 0) + 1
+            if self._good >= growth_interval and eng.S < 65536.0:
+                eng.S *= 2.0
+                self._good = 0
+        return eng.S
 
     def grad_norm(self):
         """sqrt of the last computed squared gradient norm (device tensor; no sync)."""

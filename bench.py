@@ -210,6 +210,22 @@ def run_ours(args):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
+    # same end-to-end step fed with RAW uint8 frames (ImageNorm fused into the patch gather)
+    g8 = torch.Generator().manual_seed(7 + rank)
+    host_u8 = dict(host_batch)
+    for k in ("visual_inputs", "crop_visual_inputs", "context_visual_inputs"):
+        if k in host_u8:
+            host_u8[k] = torch.randint(0, 256, tuple(host_batch[k].shape), dtype=torch.uint8, generator=g8).pin_memory()
+    h2d_u8 = batch_bytes(host_u8)
+
+    def e2e_u8_step():
+        b = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_u8.items()}
+        out = step(b)
+        return torch.stack([out[k].detach() for k in out if k.endswith("_loss") and out[k] is not None]).cpu()
+
+    e2e_u8_step()
+    ms_e2e_u8 = timed(e2e_u8_step, args.steps)
+
     # roofline of the dominant kernel: event-timed GEMM launches of one extra step (tensor bound)
     ops.GEMM_PROFILE = []
     step(dev_batch)
@@ -257,6 +273,8 @@ def run_ours(args):
         "tensor_frac_of_peak_whole_step": round(FLOP_PER_PAIR[kind] * value / world / (peaks["sustained"] * 1e12), 4),
         "e2e": {"value": round(pairs / (ms_e2e * 1e-3), 3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16 if kind == "pretrain" else 8, "ms_per_step": round(ms_e2e, 3)},
+        "e2e_uint8_inputs": {"value": round(pairs / (ms_e2e_u8 * 1e-3), 3), "unit": "pairs/s",
+                             "h2d_bytes_per_step": h2d_u8, "ms_per_step": round(ms_e2e_u8, 3)},
         "gpu_launches": int(launches),
         "ms_per_step_with_fused_adamw": round(ms_opt, 3) if ms_opt else None,
         "clocks": clocks,

@@ -113,6 +113,10 @@ int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int N, float* o
 /* PatchEmbed im2col (vit.py:233-239): frames fp32 [B,T,3,H,W] -> 16-bit [B*(1+N*T), 3*P*P], canonical token order
  * row = b*(1+N*T) + 1 + n*T + t, with a zero row in every clip's cls slot */
 int alpro_patchify(const float* frames, void* out16, int fmt, int B, int T, int H, int W, int P, void* stream);
+/* same from raw uint8 frames [B,T,3,H,W] with ImageNorm fused: (u8/255 - mean[c]) / std[c] (src/datasets/data_utils.py:437-457).
+ * mean3 / std3 are HOST pointers to 3 floats. */
+int alpro_patchify_u8(const uint8_t* frames, void* out16, int fmt, int B, int T, int H, int W, int P,
+                      const float* mean3, const float* std3, void* stream);
 /* x = cat(cls + pos[0], proj + pos[1+n] + time[t]) in 'b (n t)' order (vit.py:324-361) and its parameter gradients */
 int alpro_vit_embed_fwd(const float* proj, const float* cls, const float* pos, const float* tim, float* x, int B, int N,
                         int T, int d, void* stream);

@@ -181,6 +181,15 @@ def test_patchify_embed_pool():
     want = torch.zeros(B, Sc, 3 * P * P, device=DEV)
     want[:, 1:] = pt.permute(0, 2, 1, 3).reshape(B, N * T, -1)
     assert torch.equal(out.view(B, Sc, -1), want.to(torch.float16))           # index work: bit-exact
+    # raw uint8 frames with the input normalisation fused (ImageNorm)
+    u8 = torch.randint(0, 256, (B, T, 3, H, W), device=DEV, generator=gen, dtype=torch.uint8)
+    mean, std = (0.48, 0.45, 0.40), (0.27, 0.26, 0.28)
+    out8 = torch.empty_like(out)
+    ops.patchify_u8(u8, out8, P, mean, std)
+    nf = (u8.float() / 255.0 - torch.tensor(mean, device=DEV).view(1, 1, 3, 1, 1)) / torch.tensor(std, device=DEV).view(1, 1, 3, 1, 1)
+    ref8 = torch.empty_like(out)
+    ops.patchify(nf.contiguous(), ref8, P)
+    assert rel(out8.float(), ref8.float()) < 2e-3
     proj = torch.randn(B * Sc, d, device=DEV, generator=gen)
     cls, pos, tim = (torch.randn(s, device=DEV, generator=gen) for s in ((d,), (N + 1, d), (T, d)))
     x = torch.empty(B * Sc, d, device=DEV)
