@@ -523,6 +523,15 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
 
   const int g = lane >> 2, t = lane & 3;
   const uint32_t q_base = smem_u32(sQ), k_base = smem_u32(sK), v_base = smem_u32(sV), g_base = smem_u32(sG);
+  // per-lane ldmatrix address pieces (see sattn_fwd_kernel): fragment rows are (lane & 7) + multiples of 8
+  const int l7 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
+  uint32_t xa[4], xb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xa[i] = static_cast<uint32_t>(((2 * i + b4) ^ l7) << 4);   // A operands / transposed B operands
+    xb[i] = static_cast<uint32_t>(((2 * i + b3) ^ l7) << 4);   // plain B operands
+  }
+  const uint32_t rowA = (l7 + b3 * 8) * 128, rowB = (l7 + b4 * 8) * 128;
   const float sl2 = p.scale * LOG2E;
   const int nkb = S_pad >> 4;  // 16-wide blocks along either sequence axis
 
@@ -560,9 +569,8 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
     uint32_t qa[4][4], ga[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const int row = qt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(qa[ks], tile_addr(q_base, row, col));
-      ldsm_x4(ga[ks], tile_addr(g_base, row, col));
+      ldsm_x4(qa[ks], q_base + rowA + qt * 2048 + xa[ks]);
+      ldsm_x4(ga[ks], g_base + rowA + qt * 2048 + xa[ks]);
     }
     const float ls0 = sLse[qt * 16 + g], ls1 = sLse[qt * 16 + g + 8];
     const float D0 = sD[qt * 16 + g], D1 = sD[qt * 16 + g + 8];
@@ -576,9 +584,8 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t kf[4], vf[4];
-        const int row = kb * 16 + (lane & 7) + (lane >> 4) * 8, col = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(kf, tile_addr(k_base, row, col));
-        ldsm_x4(vf, tile_addr(v_base, row, col));
+        ldsm_x4(kf, k_base + rowB + kb * 2048 + xb[ks]);
+        ldsm_x4(vf, v_base + rowB + kb * 2048 + xb[ks]);
         mma16816<BF>(s[0], qa[ks], kf[0], kf[1]);
         mma16816<BF>(s[1], qa[ks], kf[2], kf[3]);
         mma16816<BF>(dp[0], ga[ks], vf[0], vf[1]);
@@ -604,7 +611,7 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
 #pragma unroll
       for (int dpair = 0; dpair < 4; ++dpair) {  // dQ += dS K   (B = K[key][dh], k = key -> transposed ldmatrix)
         uint32_t kb4[4];
-        ldsm_x4_t(kb4, tile_addr(k_base, kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dpair * 16 + (lane >> 4) * 8));
+        ldsm_x4_t(kb4, k_base + rowA + kb * 2048 + xa[dpair]);
         mma16816<BF>(dq[2 * dpair], da, kb4[0], kb4[1]);
         mma16816<BF>(dq[2 * dpair + 1], da, kb4[2], kb4[3]);
       }
@@ -635,9 +642,8 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
     uint32_t ka[4][4], va[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(ka[ks], tile_addr(k_base, row, col));
-      ldsm_x4(va[ks], tile_addr(v_base, row, col));
+      ldsm_x4(ka[ks], k_base + rowA + kt * 2048 + xa[ks]);
+      ldsm_x4(va[ks], v_base + rowA + kt * 2048 + xa[ks]);
     }
     const float mk0 = sMask[kt * 16 + g], mk1 = sMask[kt * 16 + g + 8];  // key = fragment row now
     float dk[8][4], dv[8][4];
@@ -650,9 +656,8 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t qf[4], gf[4];
-        const int row = qb * 16 + (lane & 7) + (lane >> 4) * 8, col = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(qf, tile_addr(q_base, row, col));
-        ldsm_x4(gf, tile_addr(g_base, row, col));
+        ldsm_x4(qf, q_base + rowB + qb * 2048 + xb[ks]);
+        ldsm_x4(gf, g_base + rowB + qb * 2048 + xb[ks]);
         mma16816<BF>(st[0], ka[ks], qf[0], qf[1]);
         mma16816<BF>(st[1], ka[ks], qf[2], qf[3]);
         mma16816<BF>(dpt[0], va[ks], gf[0], gf[1]);
@@ -690,9 +695,8 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
 #pragma unroll
       for (int dpair = 0; dpair < 4; ++dpair) {
         uint32_t gb[4], qb4[4];
-        const uint32_t off_row = qb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, off_col = dpair * 16 + (lane >> 4) * 8;
-        ldsm_x4_t(gb, tile_addr(g_base, off_row, off_col));   // dV += P^T dO
-        ldsm_x4_t(qb4, tile_addr(q_base, off_row, off_col));  // dK += dS^T Q
+        ldsm_x4_t(gb, g_base + rowA + qb * 2048 + xa[dpair]);    // dV += P^T dO
+        ldsm_x4_t(qb4, q_base + rowA + qb * 2048 + xa[dpair]);   // dK += dS^T Q
         mma16816<BF>(dv[2 * dpair], pa, gb[0], gb[1]);
         mma16816<BF>(dv[2 * dpair + 1], pa, gb[2], gb[3]);
         mma16816<BF>(dk[2 * dpair], da, qb4[0], qb4[1]);
@@ -741,6 +745,8 @@ __global__ void cls_qkv_reduce_kernel(const float* __restrict__ part, uint16_t* 
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
+  // ask for the full shared-memory carveout so that two ~100 KB CTAs fit one SM
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
     if (e != cudaSuccess) {

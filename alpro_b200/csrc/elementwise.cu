@@ -115,7 +115,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
 // Each warp walks rows with a grid stride and keeps its dgamma/dbeta partials in registers; one block-level
 // reduction + fp32 atomics at the end.
 template <int NV4>
-__global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, long long lddy,
+__global__ void __launch_bounds__(192, 3) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_kind, long long lddy,
                                      const float* __restrict__ x, long long ldx, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, const float* __restrict__ gamma, long long M,
                                      int d, float* __restrict__ dx32, long long lddx, int accumulate,
@@ -126,14 +126,21 @@ __global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __res
                                      const uint16_t* __restrict__ dx16_mul16, long long lddxmul,
                                      const float* __restrict__ dx16_row_scale,
                                      const float* __restrict__ colsum_row_scale) {
-  extern __shared__ float red[];  // [warps][d] x 2
+  // Per-warp accumulators for dgamma / dbeta / bias column sums live in shared memory ([warp][3][d], each lane owns its
+  // float4 slots -> conflict-free, no atomics) so that registers stay free for more resident warps.
+  extern __shared__ float red[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int nv = d >> 2;
-  float4 ag[NV4], ab[NV4], ac[NV4];
+  float4* ag = reinterpret_cast<float4*>(red + (warp * 3 + 0) * d);
+  float4* ab = reinterpret_cast<float4*>(red + (warp * 3 + 1) * d);
+  float4* ac = reinterpret_cast<float4*>(red + (warp * 3 + 2) * d);
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) ag[c] = ab[c] = ac[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   for (long long row = static_cast<long long>(blockIdx.x) * nwarps + warp; row < M;
        row += static_cast<long long>(gridDim.x) * nwarps) {
@@ -174,8 +181,10 @@ __global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __res
         const float gx = dv[i].x * gm.x, gy = dv[i].y * gm.y, gz = dv[i].z * gm.z, gw = dv[i].w * gm.w;
         s1 += (gx + gy) + (gz + gw);
         s2 += (gx * hx + gy * hy) + (gz * hz + gw * hw);
-        ag[i].x += dv[i].x * hx; ag[i].y += dv[i].y * hy; ag[i].z += dv[i].z * hz; ag[i].w += dv[i].w * hw;
-        ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
+        float4 a1 = ag[c], a2 = ab[c];
+        a1.x += dv[i].x * hx; a1.y += dv[i].y * hy; a1.z += dv[i].z * hz; a1.w += dv[i].w * hw;
+        a2.x += dv[i].x; a2.y += dv[i].y; a2.z += dv[i].z; a2.w += dv[i].w;
+        ag[c] = a1; ab[c] = a2;
       }
     }
     const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
@@ -205,7 +214,9 @@ __global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __res
         }
         if (cs_on) {
           const float cs = colsum_row_scale ? colsum_row_scale[row] : (dx16_row_scale ? dx16_row_scale[row] : 1.f);
-          ac[i].x += o.x * cs; ac[i].y += o.y * cs; ac[i].z += o.z * cs; ac[i].w += o.w * cs;
+          float4 a3 = ac[c];
+          a3.x += o.x * cs; a3.y += o.y * cs; a3.z += o.z * cs; a3.w += o.w * cs;
+          ac[c] = a3;
         }
         if (dx16) {
           uint2 w;
@@ -221,41 +232,17 @@ __global__ void __launch_bounds__(192, 2) layernorm_bwd_kernel(const void* __res
       }
     }
   }
-  if (colsum) {   // bias gradient of the Linear whose output gradient this dx is (column sums of the new dx)
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      const int c = lane + i * 32;
-      if (c < nv) reinterpret_cast<float4*>(red + warp * d)[c] = ac[i];
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-      float sc = 0.f;
-      for (int w = 0; w < nwarps; ++w) sc += red[w * d + c];
-      atomicAdd(colsum + c, sc * param_scale);
-    }
-    __syncthreads();
-  }
-  if (!dgamma && !dbeta) return;
-  float* rg = red;
-  float* rb = red + nwarps * d;
-#pragma unroll
-  for (int i = 0; i < NV4; ++i) {
-    const int c = lane + i * 32;
-    if (c < nv) {
-      reinterpret_cast<float4*>(rg + warp * d)[c] = ag[i];
-      reinterpret_cast<float4*>(rb + warp * d)[c] = ab[i];
-    }
-  }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float sg = 0.f, sb = 0.f;
+    float sg = 0.f, sb = 0.f, sc = 0.f;
     for (int w = 0; w < nwarps; ++w) {
-      sg += rg[w * d + c];
-      sb += rb[w * d + c];
+      sg += red[(w * 3 + 0) * d + c];
+      sb += red[(w * 3 + 1) * d + c];
+      sc += red[(w * 3 + 2) * d + c];
     }
     if (dgamma) atomicAdd(dgamma + c, sg * param_scale);
     if (dbeta) atomicAdd(dbeta + c, sb * param_scale);
+    if (colsum) atomicAdd(colsum + c, sc * param_scale);   // bias gradient of the Linear this dx belongs to
   }
 }
 
@@ -649,17 +636,22 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
   ALPRO_REQUIRE(dy_kind >= 0 && dy_kind <= 2, "alpro_layernorm_bwd: dy_kind");
   const int wpb = 6;
   int grid = static_cast<int>(cdiv(M, wpb));
-  const int cap = num_sms() * 2;   // one resident wave (2 blocks/SM): fewest same-address atomics at the end
+  const int cap = num_sms() * 3;   // one resident wave (3 blocks/SM): fewest same-address atomics at the end
   if (grid > cap) grid = cap;
-  const size_t smem = static_cast<size_t>(2) * wpb * d * sizeof(float);
+  const size_t smem = static_cast<size_t>(3) * wpb * d * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define ALPRO_LN_BWD(NV)                                                                                              \
+  do {                                                                                                                \
+  cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));  \
+  cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout,                      \
+                       cudaSharedmemCarveoutMaxShared);                                                                \
   layernorm_bwd_kernel<NV><<<grid, wpb * 32, smem, st>>>(dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, \
                                                          accumulate, static_cast<uint16_t*>(dx16), lddx16, dx16_fmt,   \
                                                          zero_period, dgamma, dbeta, param_scale, colsum,              \
                                                          colsum_zero_period, static_cast<const uint16_t*>(dy_mul16),   \
                                                          lddymul, static_cast<const uint16_t*>(dx16_mul16), lddxmul,   \
-                                                         dx16_row_scale, colsum_row_scale)
+                                                         dx16_row_scale, colsum_row_scale);            \
+  } while (0)
   if (d <= 256) ALPRO_LN_BWD(2);
   else if (d <= 768) ALPRO_LN_BWD(6);
   else ALPRO_LN_BWD(8);
