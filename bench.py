@@ -254,6 +254,18 @@ def run_ours(args):
         step_opt()
         ms_opt = timed(step_opt, max(2, args.steps // 2))
 
+    # sanity of the measured computation: losses and the gradient norm of one more step must be finite
+    chk = model(dev_batch)
+    chk_loss = sum(v for k, v in chk.items() if k.endswith("_loss") and v is not None)
+    chk_loss.backward()
+    gflat = model.engine.last_grads.flat
+    finite = bool(torch.isfinite(chk_loss).item()) and bool(torch.isfinite(gflat).all().item())
+    loss_vals = {k: round(float(v), 5) for k, v in chk.items() if k.endswith("_loss") and v is not None}
+    gnorm = float(gflat.double().norm())
+    if world > 1:
+        acomm.allreduce_gradients(model)
+    for p in model.parameters():
+        p.grad = None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -275,6 +287,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": 16 if kind == "pretrain" else 8, "ms_per_step": round(ms_e2e, 3)},
         "e2e_uint8_inputs": {"value": round(pairs / (ms_e2e_u8 * 1e-3), 3), "unit": "pairs/s",
                              "h2d_bytes_per_step": h2d_u8, "ms_per_step": round(ms_e2e_u8, 3)},
+        "finite": finite, "losses": loss_vals, "grad_norm": round(gnorm, 5),
         "gpu_launches": int(launches),
         "ms_per_step_with_fused_adamw": round(ms_opt, 3) if ms_opt else None,
         "clocks": clocks,

@@ -148,3 +148,37 @@ def test_no_cpu_fallback():
     m = modeling.AlproForVideoTextRetrieval(dict(cfg["bert"]), v)
     with pytest.raises(RuntimeError):
         m(batch)
+
+
+def test_full_width_shapes_vs_oracle():
+    """Real layer widths and sequence lengths of the bench workload (d=768/12 heads, 8x224^2 -> 1569 tokens per clip,
+    197-key spatial attention, L=40, 237-token fusion sequences, vocab 30522, 1000 entities) on a shallow stack
+    (2 TimeSformer blocks, 2+2 BERT layers) so that the CPU oracle finishes in seconds: pretrain step, fwd + bwd."""
+    from oracle import configs as C
+    cfg = C.tiny("pretrain", B=2, T=8, img=224, L=40, d=768, depth=2, heads=12, bert_layers=4, fusion_layer=2,
+                 vocab=30522, num_entities=1000, seed=21)
+    cfg["bert"]["max_position_embeddings"] = 512
+    spec, sd, batch = helpers.make_inputs(cfg)
+    sd_g, oout = helpers.oracle_run(cfg, sd, batch, requires_grad=True)
+    sum(v for k, v in oout.items() if k.endswith("_loss") and v is not None).backward()
+    model = build_cuda_model(cfg, sd)
+    out = model(to_cuda(batch))
+    assert out["_neg_video"].tolist() == oout["_neg_video"] and out["_neg_text"].tolist() == oout["_neg_text"]
+    errs = {k: helpers.rel_err(out[k].detach().float().cpu(), oout[k].detach())
+            for k in ("itc_loss", "itm_loss", "itm_scores", "mlm_loss", "mlm_scores", "mpm_loss", "mpm_logits", "mpm_labels")}
+    errs["video_embeds"] = helpers.rel_err(out["_video_embeds"].cpu(), oout["_video_embeds"].detach())
+    print("full-width", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < (EMB_TOL if k.endswith("embeds") else FWD_TOL), (k, v)
+    sum(v for k, v in out.items() if k.endswith("_loss") and v is not None).backward()
+    gmax = max(float(v.grad.abs().max()) for v in sd_g.values() if v.grad is not None)
+    bad = []
+    for n, p in model.named_parameters():
+        ref = sd_g[n].grad if n in sd_g else None
+        if n.startswith("prompter.") or ref is None or float(ref.abs().max()) < 1e-6 * gmax:
+            continue
+        assert torch.isfinite(p.grad).all(), n
+        e = helpers.rel_err(p.grad.cpu(), ref)
+        if e > 3e-2:
+            bad.append((n, e))
+    assert not bad, bad[:8]
