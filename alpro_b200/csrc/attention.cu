@@ -11,6 +11,8 @@
 //    instead of the reference's rearrange/cat copies.
 //
 // Backward kernels recompute the probabilities from the saved log-sum-exp (no SxS tensor ever reaches HBM).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "rng.cuh"
@@ -729,6 +731,189 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, tcgen05
+// Same contract as sattn_fwd_kernel, but both contractions run on the 5th-generation tensor cores:
+//   S = Q K^T : tcgen05.mma M=128, N=S_pad (<= 256), K=64   -> fp32 scores in TMEM (one TMEM lane per query row)
+//   softmax   : thread r owns query row r (tcgen05.ld of its TMEM lane), base-2 exp, fp32 row statistics
+//   O = P V   : P written as a 16-bit K-major 128B-swizzled A tile in shared memory (128 keys at a time),
+//               V consumed in place as an MN-major B operand; fp32 O accumulator in TMEM columns [0,64)
+// The gathered Q/K/V tiles already use the UMMA 128B-swizzle K-major layout, so the cp.async gather needs no repacking.
+// One CTA (4 warps) per (sequence, head), <= ~100 KB smem and 256 TMEM columns -> two CTAs per SM overlap each other's
+// load / MMA / softmax phases. 197 queries = two M=128 tiles (the second has 69 valid rows).
+template <bool BF>
+__global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) {
+  extern __shared__ uint8_t sm_raw[];
+  const uint32_t raw_addr = smem_u32(sm_raw);
+  uint8_t* sm = sm_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int S_pad = (p.S + 15) & ~15;  // dropout-mask indexing (shared with the mma.sync kernels)
+  const int S32 = (p.S + 31) & ~31;    // keys padded to whole 32-column TMEM chunks; padded K/V rows are zero
+  uint8_t* sQ = sm;                    // [128][64]  one query tile
+  uint8_t* sK = sQ + 128 * 128;        // [S32][64]
+  uint8_t* sV = sK + S32 * 128;        // [S32][64]
+  uint8_t* sP = sV + S32 * 128;        // 2 blocks of [128][64]: probabilities of 128 keys
+  float* sMask = reinterpret_cast<float*>(sP + 2 * 16384);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sMask + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, seq, S32, sK, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S32, sV, nullptr);
+  for (int j = tid; j < 256; j += 128)
+    sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this warp's TMEM lane quarter
+  const float sl2 = p.scale * LOG2E;
+  const int fmt = BF ? 1 : 0;
+  const uint32_t idesc_s = make_idesc_f16(fmt, fmt, 0, 0, 128, S32);
+  const uint32_t idesc_o = make_idesc_f16(fmt, fmt, 0, 1, 128, DH);
+  const int nks = S32 >> 4;            // 16-key steps of the PV contraction
+  const int nchunk = S32 >> 5;
+  uint32_t phase = 0;
+
+  for (int qt = 0; qt * 128 < p.S; ++qt) {
+    // ---- stage this query tile (rows beyond S are zero-filled), first tile also waits for K / V
+    {
+      const uint32_t base = smem_u32(sQ);
+      for (int idx = tid; idx < 128 * 8; idx += 128) {
+        const int row = idx >> 3, ch = idx & 7;
+        const int gr = qt * 128 + row;
+        const int rr = gr < p.S ? gr : 0;
+        const uint16_t* g = p.qkv + srow(p, seq, rr) * p.ld_qkv + head * DH + ch * 8;
+        const uint32_t nbytes = gr < p.S ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + row * 128 + ((ch ^ (row & 7)) << 4)),
+                     "l"(g), "r"(nbytes)
+                     : "memory");
+      }
+    }
+    cp_async_wait_all();
+    fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_f16(tmem, make_smem_desc_sw128(qa + ks * 32, 16, 1024), make_smem_desc_sw128(ka + ks * 32, 16, 1024),
+                 idesc_s, ks > 0 ? 1u : 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+
+    const int row = qt * 128 + tid;    // query row owned by this thread
+    // ---- pass 1: row maximum (base-2 domain)
+    float m = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), sl2, sMask[c * 32 + j]));
+    }
+    // ---- pass 2: probabilities, 128 keys at a time -> sP -> O (+)= P V
+    float l = 0.f;
+    for (int half = 0; half * 128 < S32; ++half) {
+      const int c0 = half * 4, c1 = min(nchunk, c0 + 4);
+      for (int c = c0; c < c1; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = ex2(fmaf(__uint_as_float(r[j]), sl2, sMask[c * 32 + j]) - m);   // keys >= S: mask = -inf -> 0
+          l += pv[j];
+        }
+        if (p.drop_thr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a0, a1;
+            drop_pair(p, S_pad, seq, head, row, c * 16 + j, a0, a1);
+            pv[2 * j] *= a0;
+            pv[2 * j + 1] *= a1;
+          }
+        }
+        // 32 keys = 4 chunks of 16 bytes in block (c - c0) / 2 of this half
+        uint8_t* blk = sP + ((c - c0) >> 1) * 16384 + tid * 128;
+        const int cb0 = ((c - c0) & 1) * 4;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 w;
+          w.x = pack2<BF>(pv[q4 * 8 + 0], pv[q4 * 8 + 1]); w.y = pack2<BF>(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
+          w.z = pack2<BF>(pv[q4 * 8 + 4], pv[q4 * 8 + 5]); w.w = pack2<BF>(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(blk + (((cb0 + q4) ^ (tid & 7)) << 4)) = w;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+        const int k0 = half * 8, k1 = min(nks, k0 + 8);
+        for (int ks = k0; ks < k1; ++ks) {
+          const int kl = ks - k0;
+          umma_f16(tmem, make_smem_desc_sw128(pa + (kl >> 2) * 16384 + (kl & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(va + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);           // sP may be overwritten / O may be read after this
+      phase ^= 1;
+      tc_fence_after();
+    }
+    // ---- epilogue: O row / l -> 16-bit, log-sum-exp for the backward
+    if (row < p.S) {
+      const float inv = 1.f / l;
+      uint16_t* dst = (row == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
+                                            : p.o + srow(p, seq, row) * p.ld_o + head * DH;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 w;
+          w.x = pack2<BF>(__uint_as_float(r[q4 * 8 + 0]) * inv, __uint_as_float(r[q4 * 8 + 1]) * inv);
+          w.y = pack2<BF>(__uint_as_float(r[q4 * 8 + 2]) * inv, __uint_as_float(r[q4 * 8 + 3]) * inv);
+          w.z = pack2<BF>(__uint_as_float(r[q4 * 8 + 4]) * inv, __uint_as_float(r[q4 * 8 + 5]) * inv);
+          w.w = pack2<BF>(__uint_as_float(r[q4 * 8 + 6]) * inv, __uint_as_float(r[q4 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = w;
+        }
+      }
+      if (p.lse) p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + row] = m + log2f(l);
+    } else {
+      // tcgen05.ld is warp-collective: rows beyond S still take part in the loads of their warp
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c * 32, r);
+        tmem_ld_wait();
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                   // every thread is done with TMEM / sQ before the next tile reuses them
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 // dqkv[group cls row] = sum over the group's seq_div frames of the per-sequence cls-row gradients
 __global__ void cls_qkv_reduce_kernel(const float* __restrict__ part, uint16_t* __restrict__ dqkv, long long ld,
                                       long long clip_rows, int groups, int seq_div, int d3, int fmt) {
@@ -830,9 +1015,25 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
   ALPRO_REQUIRE(o && (ld_o % 8) == 0, "alpro_seq_attn_fwd: bad output");
   p.o = static_cast<uint16_t*>(o); p.ld_o = ld_o; p.cls_o = static_cast<uint16_t*>(cls_o); p.lse = lse;
   const int S_pad = (S + 15) & ~15;
-  const size_t smem = static_cast<size_t>(S_pad) * 128 * 3 + S_pad * sizeof(float);
   dim3 grid(heads, nseq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* tc_env = getenv("ALPRO_ATTN_TC");   // read per call so tests can switch implementations
+  if (tc_env && tc_env[0] == '1') {   // tcgen05 / TMEM forward (same outputs and lse format as the mma.sync kernel)
+    const size_t S32 = (S + 31) & ~31;
+    const size_t smem_tc = 1024 + 128 * 128 + S32 * 128 * 2 + 2 * 16384 + 256 * sizeof(float) + 64;
+    if (fmt == 1) {
+      rc = set_smem(sattn_fwd_tc_kernel<true>, smem_tc);
+      if (rc) return rc;
+      sattn_fwd_tc_kernel<true><<<grid, 128, smem_tc, st>>>(p);
+    } else {
+      rc = set_smem(sattn_fwd_tc_kernel<false>, smem_tc);
+      if (rc) return rc;
+      sattn_fwd_tc_kernel<false><<<grid, 128, smem_tc, st>>>(p);
+    }
+    ALPRO_CHECK_LAUNCH("alpro_seq_attn_fwd(tcgen05)");
+    return 0;
+  }
+  const size_t smem = static_cast<size_t>(S_pad) * 128 * 3 + S_pad * sizeof(float);
 #define LAUNCH_FWD(BF, NT, EX)                                               \
   do {                                                                       \
     rc = set_smem(sattn_fwd_kernel<BF, NT, EX>, smem);                       \

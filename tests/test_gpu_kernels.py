@@ -288,8 +288,16 @@ def test_temporal_attention(T):
     assert rel(gotd[:, 1:], want) < 3e-3 and float(gotd[:, 0].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("S,dt", [(40, torch.float16), (237, torch.float16), (21, torch.bfloat16), (256, torch.float16)])
-def test_seq_attention_bert_layout(S, dt):
+@pytest.fixture(params=["mma_sync", "tcgen05"])
+def attn_impl(request, monkeypatch):
+    """Forward sequence attention has two implementations; the library reads ALPRO_ATTN_TC on every call."""
+    monkeypatch.setenv("ALPRO_ATTN_TC", "1" if request.param == "tcgen05" else "0")
+    return request.param
+
+
+@pytest.mark.parametrize("S,dt", [(40, torch.float16), (237, torch.float16), (21, torch.bfloat16), (256, torch.float16),
+                                  (197, torch.float16), (129, torch.bfloat16)])
+def test_seq_attention_bert_layout(S, dt, attn_impl):
     ops = _ops()
     nseq, heads = 3, 3
     d = heads * 64
@@ -307,6 +315,8 @@ def test_seq_attention_bert_layout(S, dt):
     refo = ref.permute(0, 2, 1, 3).reshape(nseq * S, d)
     tol = 3e-3 if dt == torch.float16 else 2e-2
     assert rel(o.float(), refo.detach()) < tol
+    sc = torch.einsum("nhid,nhjd->nhij", x[0].detach(), x[1].detach()) * scale + mask[:, None, None, :]
+    assert float((lse * math.log(2.0) - torch.logsumexp(sc, -1)).abs().max()) < 2e-3      # lse is kept in base 2
     do = torch.randn(nseq * S, d, device=DEV, generator=gen).to(dt)
     dqkv = torch.empty(nseq * S, 3 * d, device=DEV, dtype=dt)
     ops.seq_attn_bwd(qkv, mask, lse, o, None, do, dqkv, None, S, nseq, heads, 1, 1, S, scale)
@@ -316,7 +326,7 @@ def test_seq_attention_bert_layout(S, dt):
 
 
 @pytest.mark.parametrize("N,T", [(4, 2), (196, 2), (9, 4)])
-def test_seq_attention_vit_layout(N, T):
+def test_seq_attention_vit_layout(N, T, attn_impl):
     """'(b t) (h w)' spatial attention read from the canonical 'b (h w t)' rows, shared cls row, cls mean."""
     ops = _ops()
     B, heads = 2, 3
