@@ -762,6 +762,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
     fence_barrier_init();
   }
   if (warp == 0) {
+    __syncwarp();
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -814,6 +815,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
     tc_fence_after();
 
     const int row = qt * 128 + tid;    // query row owned by this thread
+    __syncwarp();                      // lane 0 of warp 0 took the MMA-issue branch: reconverge before tcgen05.ld
     // ---- pass 1: row maximum (base-2 domain)
     float m = -INFINITY;
     for (int c = 0; c < nchunk; ++c) {
@@ -874,36 +876,35 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
       mbar_wait(bar, phase);           // sP may be overwritten / O may be read after this
       phase ^= 1;
       tc_fence_after();
+      __syncwarp();
     }
-    // ---- epilogue: O row / l -> 16-bit, log-sum-exp for the backward
-    if (row < p.S) {
+    // ---- epilogue: O row / l -> 16-bit, log-sum-exp for the backward. tcgen05.ld is warp-collective (.sync.aligned):
+    // every lane executes the loads, only lanes that own a real query row store.
+    {
+      const bool valid = row < p.S;
+      const int rr = valid ? row : 0;
       const float inv = 1.f / l;
-      uint16_t* dst = (row == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
-                                            : p.o + srow(p, seq, row) * p.ld_o + head * DH;
+      uint16_t* dst = (rr == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
+                                           : p.o + srow(p, seq, rr) * p.ld_o + head * DH;
+      __syncwarp();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 w;
-          w.x = pack2<BF>(__uint_as_float(r[q4 * 8 + 0]) * inv, __uint_as_float(r[q4 * 8 + 1]) * inv);
-          w.y = pack2<BF>(__uint_as_float(r[q4 * 8 + 2]) * inv, __uint_as_float(r[q4 * 8 + 3]) * inv);
-          w.z = pack2<BF>(__uint_as_float(r[q4 * 8 + 4]) * inv, __uint_as_float(r[q4 * 8 + 5]) * inv);
-          w.w = pack2<BF>(__uint_as_float(r[q4 * 8 + 6]) * inv, __uint_as_float(r[q4 * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = w;
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 w;
+            w.x = pack2<BF>(__uint_as_float(r[q4 * 8 + 0]) * inv, __uint_as_float(r[q4 * 8 + 1]) * inv);
+            w.y = pack2<BF>(__uint_as_float(r[q4 * 8 + 2]) * inv, __uint_as_float(r[q4 * 8 + 3]) * inv);
+            w.z = pack2<BF>(__uint_as_float(r[q4 * 8 + 4]) * inv, __uint_as_float(r[q4 * 8 + 5]) * inv);
+            w.w = pack2<BF>(__uint_as_float(r[q4 * 8 + 6]) * inv, __uint_as_float(r[q4 * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = w;
+          }
         }
       }
-      if (p.lse) p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + row] = m + log2f(l);
-    } else {
-      // tcgen05.ld is warp-collective: rows beyond S still take part in the loads of their warp
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + c * 32, r);
-        tmem_ld_wait();
-      }
+      if (valid && p.lse) p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + row] = m + log2f(l);
     }
     tc_fence_before();
     __syncthreads();                   // every thread is done with TMEM / sQ before the next tile reuses them

@@ -292,7 +292,7 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D tensor map over 16-bit elements: dims {inner, outer}, 128B swizzle, zero fill out of bounds.
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
-             uint32_t box_outer) {
+             uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -303,7 +303,7 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, ui
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu pitch=%llu box=%ux%u ptr=%p", (int)r,
@@ -319,6 +319,18 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, ui
 namespace gemm2 {
 int launch_2cta(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const gemm::GemmKParams& p, int grid,
                 cudaStream_t st);
+}
+
+namespace gemm3 {
+int launch_2cta_tma_epi(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                        const CUtensorMap& tmO2, const CUtensorMap& tmAux, const gemm::GemmKParams& p, int grid,
+                        cudaStream_t st);
+}
+
+// ALPRO_GEMM_TMA_EPI=0 keeps the 16-bit output modes on the register/ST.G epilogue of gemm_tc2.cu (read per call).
+static bool use_tma_epilogue() {
+  const char* e = getenv("ALPRO_GEMM_TMA_EPI");
+  return !(e && e[0] == '0');
 }
 
 // ALPRO_GEMM_2CTA=0 selects the single-CTA kernel (default: CTA-pair kernel, cta_group::2).
@@ -420,6 +432,28 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pair) {
     const int clusters = work < num_sms() / 2 ? work : num_sms() / 2;
+    // TMA-store epilogue (gemm_tc3.cu): 16-bit outputs whose rows the TMA unit can address (16-byte aligned base and
+    // pitch), whole 32-column chunks, one storage format, no per-row scales.
+    const bool tma_epi =
+        (mode == E_OUT16 || mode == E_GELU_SAVE || mode == E_GELU_GRAD) && use_tma_epilogue() && (N % 32) == 0 &&
+        !p.rs_acc && aligned16(p.out16) && (p.ld16 % 8) == 0 && (!p.bias || aligned16(p.bias)) &&
+        (mode != E_GELU_SAVE || (p.out16b && aligned16(p.out16b) && (p.ld16b % 8) == 0 && p.out16b_fmt == p.out16_fmt)) &&
+        (mode != E_GELU_GRAD || (aligned16(p.aux16) && (p.ldaux % 8) == 0 && p.aux_fmt == p.out16_fmt));
+    if (tma_epi) {
+      CUtensorMap tmO, tmO2, tmAux;
+      rc = make_map(&tmO, p.out16, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      tmO2 = tmO;
+      tmAux = tmO;
+      if (mode == E_GELU_SAVE)
+        rc = make_map(&tmO2, p.out16b, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld16b, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (mode == E_GELU_GRAD)
+        rc = make_map(&tmAux, p.aux16, (uint64_t)N, (uint64_t)M, (uint64_t)p.ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      gemm3::launch_2cta_tma_epi(mode, tmA, tmB, tmO, tmO2, tmAux, p, 2 * clusters, st);
+      ALPRO_CHECK_LAUNCH("alpro_gemm16(2cta, tma epilogue)");
+      return 0;
+    }
     gemm2::launch_2cta(mode, tmA, tmB, p, 2 * clusters, st);
     ALPRO_CHECK_LAUNCH("alpro_gemm16(2cta)");
     return 0;
