@@ -290,19 +290,19 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D tensor map over 16-bit elements: dims {inner, outer}, 128B swizzle, zero fill out of bounds.
+// 2-D tensor map over 16-bit (or fp32) elements: dims {inner, outer}, 128B swizzle by default, zero fill out of bounds.
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
-             uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+             uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int elem_bytes = 2) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable");
     return ALPRO_EDRIVER;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint64_t strides[1] = {pitch_elems * static_cast<uint64_t>(elem_bytes)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -432,24 +432,40 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pair) {
     const int clusters = work < num_sms() / 2 ? work : num_sms() / 2;
-    // TMA-store epilogue (gemm_tc3.cu): 16-bit outputs whose rows the TMA unit can address (16-byte aligned base and
-    // pitch), whole 32-column chunks, one storage format, no per-row scales.
-    const bool tma_epi =
-        (mode == E_OUT16 || mode == E_GELU_SAVE || mode == E_GELU_GRAD) && use_tma_epilogue() && (N % 32) == 0 &&
-        !p.rs_acc && aligned16(p.out16) && (p.ld16 % 8) == 0 && (!p.bias || aligned16(p.bias)) &&
-        (mode != E_GELU_SAVE || (p.out16b && aligned16(p.out16b) && (p.ld16b % 8) == 0 && p.out16b_fmt == p.out16_fmt)) &&
-        (mode != E_GELU_GRAD || (aligned16(p.aux16) && (p.ldaux % 8) == 0 && p.aux_fmt == p.out16_fmt));
+    // TMA-store epilogue (gemm_tc3.cu): outputs (and the residual / saved-derivative input) whose rows the TMA unit can
+    // address (16-byte aligned base and pitch), whole 32-column chunks, one 16-bit storage format.
+    bool tma_epi = use_tma_epilogue() && (N % 32) == 0 && (!p.bias || aligned16(p.bias));
+    if (mode == E_OUT16 || mode == E_GELU_SAVE || mode == E_GELU_GRAD) {
+      tma_epi = tma_epi && aligned16(p.out16) && (p.ld16 % 8) == 0;
+      if (mode == E_GELU_SAVE && p.out16b)
+        tma_epi = tma_epi && aligned16(p.out16b) && (p.ld16b % 8) == 0 && p.out16b_fmt == p.out16_fmt;
+      if (mode == E_GELU_GRAD)
+        tma_epi = tma_epi && !p.rs_acc && aligned16(p.aux16) && (p.ldaux % 8) == 0 && p.aux_fmt == p.out16_fmt;
+    } else if (mode == E_RESID_OUT32) {
+      tma_epi = tma_epi && !p.out16 && aligned16(p.out32) && (p.ld32 % 4) == 0 && aligned16(p.resid) &&
+                (p.ldresid % 4) == 0;
+    } else {
+      tma_epi = false;
+    }
     if (tma_epi) {
       CUtensorMap tmO, tmO2, tmAux;
-      rc = make_map(&tmO, p.out16, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
-      tmO2 = tmO;
-      tmAux = tmO;
-      if (mode == E_GELU_SAVE)
-        rc = make_map(&tmO2, p.out16b, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld16b, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (mode == E_GELU_GRAD)
-        rc = make_map(&tmAux, p.aux16, (uint64_t)N, (uint64_t)M, (uint64_t)p.ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
+      if (mode == E_RESID_OUT32) {
+        rc = make_map(&tmO, p.out32, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld32, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, 4);
+        if (rc) return rc;
+        rc = make_map(&tmAux, p.resid, (uint64_t)N, (uint64_t)M, (uint64_t)p.ldresid, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, 4);
+        if (rc) return rc;
+        tmO2 = tmO;
+      } else {
+        rc = make_map(&tmO, p.out16, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld16, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        tmO2 = tmO;
+        tmAux = tmO;
+        if (mode == E_GELU_SAVE && p.out16b)
+          rc = make_map(&tmO2, p.out16b, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld16b, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (mode == E_GELU_GRAD)
+          rc = make_map(&tmAux, p.aux16, (uint64_t)N, (uint64_t)M, (uint64_t)p.ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
       gemm3::launch_2cta_tma_epi(mode, tmA, tmB, tmO, tmO2, tmAux, p, 2 * clusters, st);
       ALPRO_CHECK_LAUNCH("alpro_gemm16(2cta, tma epilogue)");
       return 0;

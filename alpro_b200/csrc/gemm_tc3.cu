@@ -1,6 +1,7 @@
 // gemm16_2cta_tma_epi_kernel: the CTA-pair tcgen05 GEMM of gemm_tc2.cu with a TMA-store epilogue for the 16-bit output
-// modes (E_OUT16, E_GELU_SAVE, E_GELU_GRAD) -- the modes whose K = 768 problems were bound by epilogue instruction
-// issue, not by the tensor pipe (profiles/r01f: fc1+GELU 648 TFLOP/s, fc2-dgrad*gelu' 511 TFLOP/s).
+// modes (E_OUT16, E_GELU_SAVE, E_GELU_GRAD) and the fp32 residual mode (E_RESID_OUT32) -- the modes whose K = 768
+// problems were bound by epilogue instruction issue, not by the tensor pipe (profiles/r01f: fc1+GELU 648 TFLOP/s,
+// fc2-dgrad*gelu' 511 TFLOP/s, the 768x768 projections+residual ~660 TFLOP/s).
 //
 // Differences from gemm_tc2.cu:
 //   * 16 epilogue warps (4 per TMEM lane quarter, 64 accumulator columns each) instead of 8: four resident epilogue
@@ -10,7 +11,9 @@
 //   * results are packed to 16 bit, written once to a 64B-swizzled 32x32 staging tile (conflict-free 16-byte stores)
 //     and shipped by ONE cp.async.bulk.tensor store per tile chunk; the TMA unit clips the ragged M edge;
 //   * E_GELU_GRAD reads the saved gelu'(pre) tile with a TMA load one chunk ahead (double-buffered, in-place multiply
-//     in packed 16-bit arithmetic);
+//     in packed 16-bit arithmetic); E_RESID_OUT32 does the same with 32x16 fp32 residual tiles (x + branch in place);
+//   * per-row scalars (stochastic-depth row scales, the "cls rows keep the residual" rule) cost one load per ROW here
+//     because a lane owns a row;
 //   * the TMEM accumulator is released to the MMA warp as soon as its last chunk sits in registers.
 // Pipeline: 5 smem stages of 32 KB per CTA (the sixth stage of gemm_tc2.cu pays for the second set of epilogue warps).
 #include <mutex>
@@ -63,13 +66,20 @@ __device__ __forceinline__ uint32_t mul_pack(uint32_t a, uint32_t b) {
 // CU_TENSOR_MAP_SWIZZLE_64B box expects: chunk index XOR address bits [7,9)).
 __device__ __forceinline__ uint32_t stage_off(int row, int c) { return row * 64 + ((c ^ ((row >> 1) & 3)) << 4); }
 
-// One 32-column chunk of one accumulator row (this lane's): r[] raw fp32 accumulators -> staging tile(s).
-template <int MODE, bool BF>
+// Per-row epilogue scalars of this lane's row: v = ra * acc + rb * bias (ra already includes alpha).
+struct RowScale {
+  float ra, rb;
+};
+
+// One 32-column chunk of one accumulator row (this lane's): r[] raw fp32 accumulators -> packed 16-bit results in pk[]
+// (E_OUT16: pk[0..16); E_GELU_SAVE: gelu in pk[0..16), gelu' in pk[16..32)) or, for E_GELU_GRAD, the in-place product
+// with the saved-derivative tile in buf0. RS: the row carries stochastic-depth scales (otherwise ra = alpha, rb = 1).
+template <int MODE, bool BF, bool RS>
 __device__ __forceinline__ void chunk_math(const GemmKParams& p, const uint32_t (&r)[32], int col0, int lane,
-                                           uint8_t* buf0, uint8_t* buf1, uint32_t (&pk)[32]) {
-  const float alpha = p.alpha;
+                                           uint8_t* buf0, const RowScale rs, uint32_t (&pk)[32]) {
   if (MODE == E_GELU_GRAD) {
     // out = (alpha * acc) * gelu'(pre): the saved derivative tile was TMA-loaded into buf0; multiply in place
+    const float alpha = rs.ra;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint4 a = *reinterpret_cast<const uint4*>(buf0 + stage_off(lane, g));
@@ -80,24 +90,41 @@ __device__ __forceinline__ void chunk_math(const GemmKParams& p, const uint32_t 
       *reinterpret_cast<uint4*>(buf0 + stage_off(lane, g)) = a;
     }
   } else {
-  // bias of the 32 columns: the same addresses in every lane (one broadcast transaction per float4)
+    // bias of the 32 columns: the same addresses in every lane (one broadcast transaction per float4)
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 8; ++g) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * g));
+      if (RS) { b.x *= rs.rb; b.y *= rs.rb; b.z *= rs.rb; b.w *= rs.rb; }
+      float x0 = fmaf(__uint_as_float(r[4 * g + 0]), rs.ra, b.x), x1 = fmaf(__uint_as_float(r[4 * g + 1]), rs.ra, b.y);
+      float x2 = fmaf(__uint_as_float(r[4 * g + 2]), rs.ra, b.z), x3 = fmaf(__uint_as_float(r[4 * g + 3]), rs.ra, b.w);
+      if (MODE == E_GELU_SAVE) {   // (without out16b the derivative half is dead code the compiler drops per branch)
+        float d0, d1, d2, d3;
+        gelu_erf_both(x0, x0, d0); gelu_erf_both(x1, x1, d1); gelu_erf_both(x2, x2, d2); gelu_erf_both(x3, x3, d3);
+        pk[16 + 2 * g] = cvt_pack<BF>(d0, d1);
+        pk[16 + 2 * g + 1] = cvt_pack<BF>(d2, d3);
+      }
+      pk[2 * g] = cvt_pack<BF>(x0, x1);
+      pk[2 * g + 1] = cvt_pack<BF>(x2, x3);
+    }
+  }
+}
+
+// E_RESID_OUT32: one 16-column fp32 chunk; the residual tile sits in buf (TMA-loaded), result written in place:
+//   out = resid + ra * acc + rb * bias      (rows that keep the plain residual arrive with ra = rb = 0)
+__device__ __forceinline__ void chunk_resid(const GemmKParams& p, const uint32_t (&r)[16], int col0, int lane,
+                                            uint8_t* buf, const RowScale rs) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * g));
-    float x0 = fmaf(__uint_as_float(r[4 * g + 0]), alpha, b.x), x1 = fmaf(__uint_as_float(r[4 * g + 1]), alpha, b.y);
-    float x2 = fmaf(__uint_as_float(r[4 * g + 2]), alpha, b.z), x3 = fmaf(__uint_as_float(r[4 * g + 3]), alpha, b.w);
-    if (MODE == E_GELU_SAVE) {
-      float d0, d1, d2, d3;
-      gelu_erf_both(x0, x0, d0); gelu_erf_both(x1, x1, d1); gelu_erf_both(x2, x2, d2); gelu_erf_both(x3, x3, d3);
-      pk[16 + 2 * g] = cvt_pack<BF>(d0, d1);
-      pk[16 + 2 * g + 1] = cvt_pack<BF>(d2, d3);
-    }
-    pk[2 * g] = cvt_pack<BF>(x0, x1);
-    pk[2 * g + 1] = cvt_pack<BF>(x2, x3);
+    float4 x = *reinterpret_cast<const float4*>(buf + stage_off(lane, g));
+    x.x = fmaf(__uint_as_float(r[4 * g + 0]), rs.ra, fmaf(b.x, rs.rb, x.x));
+    x.y = fmaf(__uint_as_float(r[4 * g + 1]), rs.ra, fmaf(b.y, rs.rb, x.y));
+    x.z = fmaf(__uint_as_float(r[4 * g + 2]), rs.ra, fmaf(b.z, rs.rb, x.z));
+    x.w = fmaf(__uint_as_float(r[4 * g + 3]), rs.ra, fmaf(b.w, rs.rb, x.w));
+    *reinterpret_cast<float4*>(buf + stage_off(lane, g)) = x;
   }
-  }
-  (void)buf0; (void)buf1;
 }
 
 template <int MODE>
@@ -128,7 +155,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     if (MODE == E_GELU_SAVE) tma_prefetch_desc(&tmO2);
-    if (MODE == E_GELU_GRAD) tma_prefetch_desc(&tmAux);
+    if (MODE == E_GELU_GRAD || MODE == E_RESID_OUT32) tma_prefetch_desc(&tmAux);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -226,17 +253,20 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     auto bufp = [&](uint32_t i) { return ebase + (i & 1u) * EPI_BUF_BYTES; };   // the warp's two staging tiles
     uint64_t* abar = aux_bar + 2 * ew;
     const bool bf = p.out16_fmt != 0;
+    constexpr bool LOADS = (MODE == E_GELU_GRAD || MODE == E_RESID_OUT32);   // epilogue input tile via TMA load
+    constexpr int CW = (MODE == E_RESID_OUT32) ? 16 : 32;                    // chunk width: 64-byte rows either way
+    constexpr int NCH = 64 / CW;                                             // chunks per warp and tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    // chunk (w, ch) of this warp covers columns n_blk*BN + slot*64 + ch*32 .. +32 ; valid while it starts below N
-    auto chunk_col = [&](int w, int ch) { return (w % p.num_n_tiles) * BN + slot * 64 + ch * EPI_CHUNK; };
+    // chunk (w, ch) of this warp covers columns n_blk*BN + slot*64 + ch*CW .. +CW ; valid while it starts below N
+    auto chunk_col = [&](int w, int ch) { return (w % p.num_n_tiles) * BN + slot * 64 + ch * CW; };
     auto chunk_row = [&](int w) { return (w / p.num_n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32; };
-    // E_GELU_GRAD: cursor of the NEXT chunk whose saved-derivative tile has to be requested, one chunk ahead
+    // LOADS: cursor of the NEXT chunk whose input tile has to be requested, one chunk ahead of its use
     int pw = cluster_id, pch = 0;
     uint32_t nload = 0, nuse = 0;   // chunks requested / consumed (buffer = n & 1, barrier parity = (n >> 1) & 1)
     auto request_next = [&]() {
       while (pw < num_work && chunk_col(pw, pch) >= p.N) {
-        if (++pch == 2) { pch = 0; pw += num_clusters; }
+        if (++pch == NCH) { pch = 0; pw += num_clusters; }
       }
       if (pw >= num_work) return;
       if (lane == 0) {
@@ -245,25 +275,40 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         tma_load_2d(bufp(nload), &tmAux, &abar[nload & 1], chunk_col(pw, pch), chunk_row(pw));
       }
       ++nload;
-      if (++pch == 2) { pch = 0; pw += num_clusters; }
+      if (++pch == NCH) { pch = 0; pw += num_clusters; }
     };
-    if (MODE == E_GELU_GRAD) request_next();
+    if (LOADS) request_next();
 
     for (int w = cluster_id; w < num_work; w += num_clusters) {
+      const int row0 = chunk_row(w);
+      // per-row scalars of this lane's row (clamped row index for the loads; the TMA store clips rows >= M)
+      RowScale rs;
+      rs.ra = p.alpha;
+      rs.rb = 1.f;
+      if (MODE != E_GELU_GRAD) {
+        const int row = min(row0 + lane, p.M - 1);
+        if (p.rs_acc) {
+          const float ra = __ldg(p.rs_acc + row);
+          rs.rb = p.rs_bias ? __ldg(p.rs_bias + row) : ra;
+          rs.ra *= ra;
+        }
+        if (MODE == E_RESID_OUT32 && p.skip_period > 0 && (row % p.skip_period) == 0) rs.ra = rs.rb = 0.f;
+      }
+      const bool row_scaled = p.rs_acc != nullptr;   // warp-uniform
+      const int nvalid = min(NCH, max(0, (p.N - chunk_col(w, 0) + CW - 1) / CW));   // warp-uniform
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = chunk_row(w);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN) +
                              static_cast<uint32_t>(slot * 64);
-      const bool v0 = chunk_col(w, 0) < p.N, v1 = chunk_col(w, 1) < p.N;   // warp-uniform
 #pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const bool valid = ch ? v1 : v0;
-        const bool last = v1 ? ch == 1 : ch == 0;   // exactly one release per tile, after this warp's last TMEM read
-        uint32_t r[32], pk[32];
+      for (int ch = 0; ch < NCH; ++ch) {
+        const bool valid = ch < nvalid;
+        const bool last = ch == max(nvalid, 1) - 1;   // exactly one release per tile, after this warp's last TMEM read
+        uint32_t r[CW], pk[32];
         if (valid) {
-          tmem_ld_32x32(taddr + ch * EPI_CHUNK, r);
-          if (MODE == E_GELU_GRAD) request_next();     // keep the next derivative tile in flight
+          if (CW == 32) tmem_ld_32x32(taddr + ch * CW, reinterpret_cast<uint32_t (&)[32]>(r));
+          else          tmem_ld_32x16(taddr + ch * CW, reinterpret_cast<uint32_t (&)[16]>(r));
+          if (LOADS) request_next();     // keep the next input tile in flight
           tmem_ld_wait();
         }
         if (last) {   // every column this warp needs from the accumulator is in registers: hand it back to the MMA warp
@@ -271,18 +316,30 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
         }
-        if (!valid) continue;
+        if (!valid) {
+          if (last) break;
+          continue;
+        }
         const int col0 = chunk_col(w, ch);
         uint8_t* b0;
-        if (MODE == E_GELU_GRAD) {
+        if (LOADS) {
           b0 = bufp(nuse);
           mbar_wait(&abar[nuse & 1], (nuse >> 1) & 1);
-          if (bf) chunk_math<MODE, true>(p, r, col0, lane, b0, nullptr, pk);
-          else    chunk_math<MODE, false>(p, r, col0, lane, b0, nullptr, pk);
+          if (MODE == E_RESID_OUT32) {
+            chunk_resid(p, reinterpret_cast<const uint32_t (&)[16]>(r), col0, lane, b0, rs);
+          } else {
+            if (bf) chunk_math<MODE, true, false>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, b0, rs, pk);
+            else    chunk_math<MODE, false, false>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, b0, rs, pk);
+          }
           ++nuse;
         } else {
-          if (bf) chunk_math<MODE, true>(p, r, col0, lane, nullptr, nullptr, pk);
-          else    chunk_math<MODE, false>(p, r, col0, lane, nullptr, nullptr, pk);
+          if (row_scaled) {
+            if (bf) chunk_math<MODE, true, true>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, nullptr, rs, pk);
+            else    chunk_math<MODE, false, true>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, nullptr, rs, pk);
+          } else {
+            if (bf) chunk_math<MODE, true, false>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, nullptr, rs, pk);
+            else    chunk_math<MODE, false, false>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, nullptr, rs, pk);
+          }
           // staging tiles free again? E_OUT16 alternates its two tiles, E_GELU_SAVE fills both per chunk
           if (lane == 0) {
             if (MODE == E_GELU_SAVE) bulk_wait_read<0>();
@@ -294,7 +351,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(b0 + stage_off(lane, g)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          if (MODE == E_GELU_SAVE) {
+          if (MODE == E_GELU_SAVE && p.out16b) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               *reinterpret_cast<uint4*>(bufp(1) + stage_off(lane, g)) =
@@ -305,7 +362,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         __syncwarp();
         if (lane == 0) {
           tma_store_2d(&tmO, b0, col0, row0);
-          if (MODE == E_GELU_SAVE) tma_store_2d(&tmO2, bufp(1), col0, row0);
+          if (MODE == E_GELU_SAVE && p.out16b) tma_store_2d(&tmO2, bufp(1), col0, row0);
           bulk_commit();
         }
       }
@@ -342,6 +399,7 @@ int launch_2cta_tma_epi(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB
     case E_OUT16: return launch_mode<E_OUT16>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
     case E_GELU_SAVE: return launch_mode<E_GELU_SAVE>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
     case E_GELU_GRAD: return launch_mode<E_GELU_GRAD>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
+    case E_RESID_OUT32: return launch_mode<E_RESID_OUT32>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
     default: return -1;
   }
 }

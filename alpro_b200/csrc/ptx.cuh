@@ -124,6 +124,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- cluster / cta_group::2 variants
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -229,17 +240,19 @@ __device__ __forceinline__ float erf_fast(float x) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 // gelu(x) and gelu'(x) = Phi(x) + x*phi(x) from ONE exponential: exp(-(x/sqrt2)^2) of the erf formula is exp(-x^2/2).
 __device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
-  const float z = x * 0.70710678118654752f;
-  const float az = fabsf(z);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = __expf(-az * az);                 // = exp(-x^2/2)
-  const float erfv = copysignf(1.0f - poly * t * e, z);
-  const float cdf = 0.5f * (1.0f + erfv);
+  // Phi(x) through A&S 7.1.26 on z = x/sqrt(2), with every constant folded so that the chain is 17 issue slots:
+  //   t = 1 / (1 + (p/sqrt2)|x|),  h = 0.5 * poly(t) * exp(-x^2/2)  (= 1 - Phi(|x|)),  Phi(x) = x >= 0 ? 1 - h : h
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2316418882f, fabsf(x), 1.0f)));
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  poly *= t;
+  const float w = x * 0.8493218003f;                  // (x * sqrt(log2(e)/2))^2 = x^2/2 * log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(w * w)));   // = exp(-x^2/2), one MUFU, no range fix-up code
+  const float h = poly * e;
+  const float cdf = x >= 0.f ? 1.0f - h : h;
   y = x * cdf;
   dy = fmaf(x * 0.3989422804014327f, e, cdf);
 }
