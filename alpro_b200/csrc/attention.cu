@@ -89,13 +89,34 @@ __device__ __forceinline__ float part_sum(float v) {
 }
 
 // Stage T rows x 64 dims of one 16-bit matrix into fp32 shared memory (coalesced 128-byte row reads).
+// Shared-memory rows of the temporal backward are stored PERMUTED so that the PARTS lanes of one query row read one
+// contiguous 16*PARTS-byte span with 128-bit loads (conflict-free; the straightforward [t][64] layout made the four
+// parts of T = 8 collide pairwise on every scalar read: 49M bank conflicts per launch, ncu r01j):
+//   element e = part * DPP + VW * kv + c   lives at   kv * (VW * PARTS) + VW * part + c      (VW = min(4, DPP))
 template <int T>
 __device__ __forceinline__ void tattn_stage(const uint16_t* src, long long ld, int fmt, int lane, float (*dst)[DH]) {
+  constexpr int PARTS = 32 / T, DPP = DH / PARTS, VW = DPP < 4 ? DPP : 4;
+  const int e = lane * 2;
+  const int pos = ((e % DPP) / VW) * (VW * PARTS) + (e / DPP) * VW + (e % VW);
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(src + t * ld + lane * 2);
-    dst[t][lane * 2] = f16_to_32(static_cast<uint16_t>(w & 0xffff), fmt);
-    dst[t][lane * 2 + 1] = f16_to_32(static_cast<uint16_t>(w >> 16), fmt);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(src + t * ld + e);
+    *reinterpret_cast<float2*>(&dst[t][pos]) =
+        make_float2(f16_to_32(static_cast<uint16_t>(w & 0xffff), fmt), f16_to_32(static_cast<uint16_t>(w >> 16), fmt));
+  }
+}
+// this lane's DPP-wide slice (its `part`) of one staged row
+template <int DPP, int PARTS>
+__device__ __forceinline__ void tattn_ld_part(const float* row, int part, float (&out)[DPP]) {
+  if (DPP >= 4) {
+#pragma unroll
+    for (int k4 = 0; k4 < DPP / 4; ++k4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + k4 * (4 * PARTS) + part * 4);
+      out[4 * k4] = v.x; out[(4 * k4 + 1) % DPP] = v.y; out[(4 * k4 + 2) % DPP] = v.z; out[(4 * k4 + 3) % DPP] = v.w;
+    }
+  } else {   // DPP == 2 (T = 1)
+    const float2 v = *reinterpret_cast<const float2*>(row + part * 2);
+    out[0] = v.x; out[1 % DPP] = v.y;
   }
 }
 
@@ -106,9 +127,10 @@ __device__ __forceinline__ void tattn_row_probs(const float (&q)[DPP], const flo
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < T; ++j) {
-    float s = 0.f;
+    float s = 0.f, kk[DPP];
+    tattn_ld_part<DPP, PARTS>(sk[j], part, kk);
 #pragma unroll
-    for (int e = 0; e < DPP; ++e) s += q[e] * sk[j][part * DPP + e];
+    for (int e = 0; e < DPP; ++e) s += q[e] * kk[e];
     pr[j] = part_sum<PARTS>(s) * scale;
     mx = fmaxf(mx, pr[j]);
   }
@@ -186,7 +208,8 @@ __global__ void __launch_bounds__(128, 3) tattn_fwd_kernel(const TAttnParams p) 
 template <int T>
 __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) {
   constexpr int PARTS = 32 / T, DPP = DH / PARTS, WPB = 4;
-  __shared__ float sQ[WPB][T][DH], sK[WPB][T][DH], sV[WPB][T][DH], sG[WPB][T][DH], sP[WPB][T][T], sDS[WPB][T][T];
+  __shared__ __align__(16) float sQ[WPB][T][DH], sK[WPB][T][DH], sV[WPB][T][DH], sG[WPB][T][DH];
+  __shared__ float sP[WPB][T][T], sDS[WPB][T][T];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long unit = static_cast<long long>(blockIdx.x) * WPB + wib;
   const long long total = static_cast<long long>(p.B) * p.N * p.heads;
@@ -211,18 +234,16 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
   __syncwarp();
   const int i = lane / PARTS, part = lane % PARTS;
   float q[DPP], go[DPP], pr[T];
-#pragma unroll
-  for (int e = 0; e < DPP; ++e) {
-    q[e] = sQ[wib][i][part * DPP + e];
-    go[e] = sG[wib][i][part * DPP + e];
-  }
+  tattn_ld_part<DPP, PARTS>(sQ[wib][i], part, q);
+  tattn_ld_part<DPP, PARTS>(sG[wib][i], part, go);
   tattn_row_probs<T, DPP, PARTS>(q, sK[wib], part, p.scale, pr);
   float dp[T], dot = 0.f;
 #pragma unroll
   for (int j = 0; j < T; ++j) {
-    float sdot = 0.f;
+    float sdot = 0.f, vv[DPP];
+    tattn_ld_part<DPP, PARTS>(sV[wib][j], part, vv);
 #pragma unroll
-    for (int e = 0; e < DPP; ++e) sdot += go[e] * sV[wib][j][part * DPP + e];
+    for (int e = 0; e < DPP; ++e) sdot += go[e] * vv[e];
     dp[j] = part_sum<PARTS>(sdot);
     dot += dp[j] * pr[j];
   }
@@ -236,26 +257,41 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
       sP[wib][i][j] = pr[j];
       sDS[wib][i][j] = ds;
     }
+    float kk[DPP];
+    tattn_ld_part<DPP, PARTS>(sK[wib][j], part, kk);
 #pragma unroll
-    for (int e = 0; e < DPP; ++e) dq[e] += ds * sK[wib][j][part * DPP + e];
+    for (int e = 0; e < DPP; ++e) dq[e] += ds * kk[e];
   }
   uint16_t* o = p.out + (row0 + i) * p.ld_out + head * DH + part * DPP;
   st16<DPP>(o, dq, p.fmt);
   __syncwarp();
   // role switch: this lane now owns key/value row j = i
-  float dk[DPP], dv[DPP];
+  // (two passes so that only one accumulator + one operand slice is live at a time: 128-register budget)
+  {
+    float dk[DPP];
 #pragma unroll
-  for (int e = 0; e < DPP; ++e) dk[e] = dv[e] = 0.f;
+    for (int e = 0; e < DPP; ++e) dk[e] = 0.f;
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      const float ds = sDS[wib][r][i];
+      float qq[DPP];
+      tattn_ld_part<DPP, PARTS>(sQ[wib][r], part, qq);
+#pragma unroll
+      for (int e = 0; e < DPP; ++e) dk[e] += ds * qq[e];
+    }
+    st16<DPP>(o + p.d, dk, p.fmt);
+  }
+  float dv[DPP];
+#pragma unroll
+  for (int e = 0; e < DPP; ++e) dv[e] = 0.f;
 #pragma unroll
   for (int r = 0; r < T; ++r) {
-    const float ds = sDS[wib][r][i], pp = sP[wib][r][i];
+    const float pp = sP[wib][r][i];
+    float gg[DPP];
+    tattn_ld_part<DPP, PARTS>(sG[wib][r], part, gg);
 #pragma unroll
-    for (int e = 0; e < DPP; ++e) {
-      dk[e] += ds * sQ[wib][r][part * DPP + e];
-      dv[e] += pp * sG[wib][r][part * DPP + e];
-    }
+    for (int e = 0; e < DPP; ++e) dv[e] += pp * gg[e];
   }
-  st16<DPP>(o + p.d, dk, p.fmt);
   st16<DPP>(o + 2 * p.d, dv, p.fmt);
 }
 
@@ -294,9 +330,22 @@ __device__ __forceinline__ void drop_pair(const SAttnParams& p, int S_pad, int s
   m1 = (h >> 16) >= p.drop_thr ? p.drop_scale : 0.f;
 }
 
-__device__ __forceinline__ long long srow(const SAttnParams& p, int seq, int j) {
-  const long long base = static_cast<long long>(seq / p.seq_div) * p.clip_rows;
-  return j == 0 ? base : base + 1 + (seq % p.seq_div) + static_cast<long long>(j - 1) * p.stride;
+// Canonical row of token j of one sequence: row(seq, j) = (seq / seq_div) * clip_rows + (j == 0 ? 0 : 1 + seq % seq_div +
+// (j-1) * stride). The division / modulo by the run-time seq_div is done ONCE per CTA (it was 16% of the backward's
+// instructions when evaluated per access, ncu r01j).
+struct SeqRows {
+  long long base, first;
+  int stride;
+  __device__ __forceinline__ long long operator()(int j) const {
+    return j == 0 ? base : first + static_cast<long long>(j - 1) * stride;
+  }
+};
+__device__ __forceinline__ SeqRows make_rows(const SAttnParams& p, int seq) {
+  SeqRows r;
+  r.base = static_cast<long long>(seq / p.seq_div) * p.clip_rows;
+  r.first = r.base + 1 + (seq % p.seq_div);
+  r.stride = p.stride;
+  return r;
 }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -330,14 +379,14 @@ __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int col) {
 // Cooperative gather of one [S_pad][64] tile (q, k or v columns of qkv, or a plain [rows, ld] matrix) with 16-byte
 // cp.async copies: every thread keeps all of its copies in flight (no register staging), rows >= S are zero-filled
 // through the src-size operand. Completion: cp_async_wait_all() + __syncthreads().
-__device__ __forceinline__ void load_tile(const SAttnParams& p, const uint16_t* src, long long ld, int col0, int seq,
-                                          int S_pad, uint8_t* smem_tile, const uint16_t* tok0_override) {
+__device__ __forceinline__ void load_tile(const SAttnParams& p, const uint16_t* src, long long ld, int col0,
+                                          const SeqRows& rows, int S_pad, uint8_t* smem_tile, const uint16_t* tok0_override) {
   const uint32_t base = smem_u32(smem_tile);
   for (int idx = threadIdx.x; idx < S_pad * 8; idx += blockDim.x) {
     const int row = idx >> 3, ch = idx & 7;
     const int rr = row < p.S ? row : 0;   // clamped (the copy reads 0 bytes for padded rows)
     const uint16_t* g = (rr == 0 && tok0_override) ? tok0_override + ch * 8
-                                                    : src + srow(p, seq, rr) * ld + col0 + ch * 8;
+                                                    : src + rows(rr) * ld + col0 + ch * 8;
     const uint32_t nbytes = row < p.S ? 16u : 0u;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + row * 128 + ((ch ^ (row & 7)) << 4)),
                  "l"(g), "r"(nbytes)
@@ -356,14 +405,15 @@ template <bool BF, int NT, bool EXACT>
 __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
   extern __shared__ __align__(128) uint8_t sm[];
   const int head = blockIdx.x, seq = blockIdx.y;
+  const SeqRows rows = make_rows(p, seq);
   const int S_pad = (p.S + 15) & ~15;
   uint8_t* sQ = sm;
   uint8_t* sK = sQ + S_pad * 128;
   uint8_t* sV = sK + S_pad * 128;
   float* sMask = reinterpret_cast<float*>(sV + S_pad * 128);
-  load_tile(p, p.qkv, p.ld_qkv, head * DH, seq, S_pad, sQ, nullptr);
-  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, seq, S_pad, sK, nullptr);
-  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S_pad, sV, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, head * DH, rows, S_pad, sQ, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, rows, S_pad, sK, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, rows, S_pad, sV, nullptr);
   for (int j = threadIdx.x; j < S_pad; j += blockDim.x)
     sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
   cp_async_wait_all();
@@ -473,7 +523,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
       if (r < p.S) {
         const float inv = half ? i1 : i0;
         uint16_t* dst = (r == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
-                                            : p.o + srow(p, seq, r) * p.ld_o + head * DH;
+                                            : p.o + rows(r) * p.ld_o + head * DH;
 #pragma unroll
         for (int n = 0; n < 8; ++n)
           *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * t) =
@@ -492,6 +542,7 @@ template <bool BF>
 __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) {
   extern __shared__ __align__(128) uint8_t sm[];
   const int head = blockIdx.x, seq = blockIdx.y;
+  const SeqRows rows = make_rows(p, seq);
   const int S_pad = (p.S + 15) & ~15;
   uint8_t* sQ = sm;
   uint8_t* sK = sQ + S_pad * 128;
@@ -500,10 +551,10 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
   float* sMask = reinterpret_cast<float*>(sG + S_pad * 128);
   float* sLse = sMask + S_pad;
   float* sD = sLse + S_pad;
-  load_tile(p, p.qkv, p.ld_qkv, head * DH, seq, S_pad, sQ, nullptr);
-  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, seq, S_pad, sK, nullptr);
-  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S_pad, sV, nullptr);
-  load_tile(p, p.dout, p.ld_o, head * DH, seq, S_pad, sG, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, head * DH, rows, S_pad, sQ, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, rows, S_pad, sK, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, rows, S_pad, sV, nullptr);
+  load_tile(p, p.dout, p.ld_o, head * DH, rows, S_pad, sG, nullptr);
   const float gscale0 = p.cls_weight ? p.cls_weight[seq] : 1.f / p.seq_div;  // d(weighted mean_t cls_t) / d cls_t
   for (int j = threadIdx.x; j < S_pad; j += blockDim.x) {
     sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
@@ -547,7 +598,7 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
       wo[u] = 0u;
       if (r < p.S) {
         const uint16_t* orow = (r == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
-                                                          : p.o_fwd + srow(p, seq, r) * p.ld_o + head * DH;
+                                                          : p.o_fwd + rows(r) * p.ld_o + head * DH;
         wo[u] = *reinterpret_cast<const uint32_t*>(orow + lane * 2);
       }
     }
@@ -630,7 +681,7 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
             dst[n * 8 + 2 * t + 1] = dq[n][half * 2 + 1];
           }
         } else {
-          uint16_t* dst = p.dqkv + srow(p, seq, r) * p.ld_qkv + head * DH;
+          uint16_t* dst = p.dqkv + rows(r) * p.ld_qkv + head * DH;
 #pragma unroll
           for (int n = 0; n < 8; ++n)
             *reinterpret_cast<uint32_t*>(dst + n * 8 + 2 * t) = pack2<BF>(dq[n][half * 2], dq[n][half * 2 + 1]);
@@ -719,7 +770,7 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
             dst[2 * p.d + n * 8 + 2 * t + 1] = dv[n][half * 2 + 1];
           }
         } else {
-          uint16_t* dst = p.dqkv + srow(p, seq, r) * p.ld_qkv + head * DH;
+          uint16_t* dst = p.dqkv + rows(r) * p.ld_qkv + head * DH;
 #pragma unroll
           for (int n = 0; n < 8; ++n) {
             *reinterpret_cast<uint32_t*>(dst + p.d + n * 8 + 2 * t) = pack2<BF>(dk[n][half * 2], dk[n][half * 2 + 1]);
@@ -746,6 +797,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
   const uint32_t raw_addr = smem_u32(sm_raw);
   uint8_t* sm = sm_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int head = blockIdx.x, seq = blockIdx.y;
+  const SeqRows rows = make_rows(p, seq);
   const int S_pad = (p.S + 15) & ~15;  // dropout-mask indexing (shared with the mma.sync kernels)
   const int S32 = (p.S + 31) & ~31;    // keys padded to whole 32-column TMEM chunks; padded K/V rows are zero
   uint8_t* sQ = sm;                    // [128][64]  one query tile
@@ -766,8 +818,8 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
-  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, seq, S32, sK, nullptr);
-  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, seq, S32, sV, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, rows, S32, sK, nullptr);
+  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, rows, S32, sV, nullptr);
   for (int j = tid; j < 256; j += 128)
     sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
   tc_fence_before();
@@ -791,7 +843,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
         const int row = idx >> 3, ch = idx & 7;
         const int gr = qt * 128 + row;
         const int rr = gr < p.S ? gr : 0;
-        const uint16_t* g = p.qkv + srow(p, seq, rr) * p.ld_qkv + head * DH + ch * 8;
+        const uint16_t* g = p.qkv + rows(rr) * p.ld_qkv + head * DH + ch * 8;
         const uint32_t nbytes = gr < p.S ? 16u : 0u;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + row * 128 + ((ch ^ (row & 7)) << 4)),
                      "l"(g), "r"(nbytes)
@@ -885,7 +937,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
       const int rr = valid ? row : 0;
       const float inv = 1.f / l;
       uint16_t* dst = (rr == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
-                                           : p.o + srow(p, seq, rr) * p.ld_o + head * DH;
+                                           : p.o + rows(rr) * p.ld_o + head * DH;
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
