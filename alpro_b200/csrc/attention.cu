@@ -42,8 +42,29 @@ struct TAttnParams {
 // Lane mapping: lane = (i, part) with i = query/frame index (T of them) and `part` one of 32/T slices of the 64 head
 // dims. A lane holds q_i[slice] and k_j[slice], v_j[slice] for all j, so every score needs only log2(32/T) shuffles
 // (16 per warp for T=8) and the PV product is lane-local.
-template <int DPP>
-__device__ __forceinline__ void ld16(const uint16_t* ptr, float (&out)[DPP], int fmt) {
+// 16-bit pair <-> fp32 with the storage format as a template parameter: one instruction per element (HADD2.F32 on a
+// half of the packed register / a shift), where the run-time-format helpers of ptx.cuh cost three.
+template <bool BF>
+__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi) {
+  if (BF) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x;
+    hi = f.y;
+  }
+}
+template <bool BF>
+__device__ __forceinline__ uint32_t pack2c(float lo, float hi) {
+  uint32_t d;
+  if (BF) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+template <int DPP, bool BF>
+__device__ __forceinline__ void ld16(const uint16_t* ptr, float (&out)[DPP]) {
   uint32_t w[DPP / 2];
   if (DPP == 16) {
     const uint4 a = *reinterpret_cast<const uint4*>(ptr);
@@ -60,16 +81,13 @@ __device__ __forceinline__ void ld16(const uint16_t* ptr, float (&out)[DPP], int
     w[0] = *reinterpret_cast<const uint32_t*>(ptr);
   }
 #pragma unroll
-  for (int j = 0; j < DPP / 2; ++j) {
-    out[2 * j] = f16_to_32(static_cast<uint16_t>(w[j] & 0xffff), fmt);
-    out[2 * j + 1] = f16_to_32(static_cast<uint16_t>(w[j] >> 16), fmt);
-  }
+  for (int j = 0; j < DPP / 2; ++j) unpack2<BF>(w[j], out[2 * j], out[2 * j + 1]);
 }
-template <int DPP>
-__device__ __forceinline__ void st16(uint16_t* ptr, const float (&v)[DPP], int fmt) {
+template <int DPP, bool BF>
+__device__ __forceinline__ void st16(uint16_t* ptr, const float (&v)[DPP]) {
   uint32_t w[DPP / 2];
 #pragma unroll
-  for (int j = 0; j < DPP / 2; ++j) w[j] = pack2_16(v[2 * j], v[2 * j + 1], fmt);
+  for (int j = 0; j < DPP / 2; ++j) w[j] = pack2c<BF>(v[2 * j], v[2 * j + 1]);
   if (DPP == 16) {
     *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4*>(ptr + 8) = make_uint4(w[4 % (DPP / 2)], w[5 % (DPP / 2)], w[6 % (DPP / 2)], w[7 % (DPP / 2)]);
@@ -93,16 +111,17 @@ __device__ __forceinline__ float part_sum(float v) {
 // contiguous 16*PARTS-byte span with 128-bit loads (conflict-free; the straightforward [t][64] layout made the four
 // parts of T = 8 collide pairwise on every scalar read: 49M bank conflicts per launch, ncu r01j):
 //   element e = part * DPP + VW * kv + c   lives at   kv * (VW * PARTS) + VW * part + c      (VW = min(4, DPP))
-template <int T>
-__device__ __forceinline__ void tattn_stage(const uint16_t* src, long long ld, int fmt, int lane, float (*dst)[DH]) {
+template <int T, bool BF>
+__device__ __forceinline__ void tattn_stage(const uint16_t* src, long long ld, int lane, float (*dst)[DH]) {
   constexpr int PARTS = 32 / T, DPP = DH / PARTS, VW = DPP < 4 ? DPP : 4;
   const int e = lane * 2;
   const int pos = ((e % DPP) / VW) * (VW * PARTS) + (e / DPP) * VW + (e % VW);
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const uint32_t w = *reinterpret_cast<const uint32_t*>(src + t * ld + e);
-    *reinterpret_cast<float2*>(&dst[t][pos]) =
-        make_float2(f16_to_32(static_cast<uint16_t>(w & 0xffff), fmt), f16_to_32(static_cast<uint16_t>(w >> 16), fmt));
+    float2 f;
+    unpack2<BF>(w, f.x, f.y);
+    *reinterpret_cast<float2*>(&dst[t][pos]) = f;
   }
 }
 // this lane's DPP-wide slice (its `part`) of one staged row
@@ -170,7 +189,7 @@ __device__ __forceinline__ void tattn_row_probs_reg(const float (&q)[DPP], const
 }
 
 // grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by the n==0 warps.
-template <int T>
+template <int T, bool BF>
 __global__ void __launch_bounds__(128, 3) tattn_fwd_kernel(const TAttnParams p) {
   constexpr int PARTS = 32 / T, DPP = DH / PARTS;
   const int lane = threadIdx.x & 31;
@@ -187,11 +206,11 @@ __global__ void __launch_bounds__(128, 3) tattn_fwd_kernel(const TAttnParams p) 
   const int i = lane / PARTS, part = lane % PARTS;
   const int coff = head * DH + part * DPP;
   float q[DPP], k[T][DPP], v[T][DPP], pr[T];
-  ld16<DPP>(p.qkv + (row0 + i) * p.ld_qkv + coff, q, p.fmt);
+  ld16<DPP, BF>(p.qkv + (row0 + i) * p.ld_qkv + coff, q);
 #pragma unroll
   for (int j = 0; j < T; ++j) {
-    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, k[j], p.fmt);
-    ld16<DPP>(p.qkv + (row0 + j) * p.ld_qkv + 2 * p.d + coff, v[j], p.fmt);
+    ld16<DPP, BF>(p.qkv + (row0 + j) * p.ld_qkv + p.d + coff, k[j]);
+    ld16<DPP, BF>(p.qkv + (row0 + j) * p.ld_qkv + 2 * p.d + coff, v[j]);
   }
   tattn_row_probs_reg<T, DPP, PARTS>(q, k, p.scale, pr);
   float o[DPP];
@@ -202,10 +221,10 @@ __global__ void __launch_bounds__(128, 3) tattn_fwd_kernel(const TAttnParams p) 
     for (int j = 0; j < T; ++j) a += pr[j] * v[j][e];
     o[e] = a;
   }
-  st16<DPP>(p.out + (row0 + i) * p.ld_out + coff, o, p.fmt);
+  st16<DPP, BF>(p.out + (row0 + i) * p.ld_out + coff, o);
 }
 
-template <int T>
+template <int T, bool BF>
 __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) {
   constexpr int PARTS = 32 / T, DPP = DH / PARTS, WPB = 4;
   __shared__ __align__(16) float sQ[WPB][T][DH], sK[WPB][T][DH], sV[WPB][T][DH], sG[WPB][T][DH];
@@ -227,10 +246,10 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
     *reinterpret_cast<uint32_t*>(z + 2 * p.d) = 0u;
   }
   const uint16_t* base = p.qkv + row0 * p.ld_qkv + head * DH;
-  tattn_stage<T>(base, p.ld_qkv, p.fmt, lane, sQ[wib]);
-  tattn_stage<T>(base + p.d, p.ld_qkv, p.fmt, lane, sK[wib]);
-  tattn_stage<T>(base + 2 * p.d, p.ld_qkv, p.fmt, lane, sV[wib]);
-  tattn_stage<T>(p.dout + row0 * p.ld_dout + head * DH, p.ld_dout, p.fmt, lane, sG[wib]);
+  tattn_stage<T, BF>(base, p.ld_qkv, lane, sQ[wib]);
+  tattn_stage<T, BF>(base + p.d, p.ld_qkv, lane, sK[wib]);
+  tattn_stage<T, BF>(base + 2 * p.d, p.ld_qkv, lane, sV[wib]);
+  tattn_stage<T, BF>(p.dout + row0 * p.ld_dout + head * DH, p.ld_dout, lane, sG[wib]);
   __syncwarp();
   const int i = lane / PARTS, part = lane % PARTS;
   float q[DPP], go[DPP], pr[T];
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
     for (int e = 0; e < DPP; ++e) dq[e] += ds * kk[e];
   }
   uint16_t* o = p.out + (row0 + i) * p.ld_out + head * DH + part * DPP;
-  st16<DPP>(o, dq, p.fmt);
+  st16<DPP, BF>(o, dq);
   __syncwarp();
   // role switch: this lane now owns key/value row j = i
   // (two passes so that only one accumulator + one operand slice is live at a time: 128-register budget)
@@ -279,7 +298,7 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
 #pragma unroll
       for (int e = 0; e < DPP; ++e) dk[e] += ds * qq[e];
     }
-    st16<DPP>(o + p.d, dk, p.fmt);
+    st16<DPP, BF>(o + p.d, dk);
   }
   float dv[DPP];
 #pragma unroll
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) 
 #pragma unroll
     for (int e = 0; e < DPP; ++e) dv[e] += pp * gg[e];
   }
-  st16<DPP>(o + 2 * p.d, dv, p.fmt);
+  st16<DPP, BF>(o + 2 * p.d, dv);
 }
 
 // ================================================================================================ sequence attention
@@ -1011,10 +1030,22 @@ extern "C" int alpro_temporal_attn_fwd(const void* qkv, int64_t ld_qkv, void* ou
   const unsigned grid = static_cast<unsigned>(cdiv(units, wpb));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (T) {
-    case 1: tattn_fwd_kernel<1><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 2: tattn_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 4: tattn_fwd_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 8: tattn_fwd_kernel<8><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 1:
+      if (fmt) tattn_fwd_kernel<1, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_fwd_kernel<1, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
+    case 2:
+      if (fmt) tattn_fwd_kernel<2, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_fwd_kernel<2, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
+    case 4:
+      if (fmt) tattn_fwd_kernel<4, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_fwd_kernel<4, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
+    case 8:
+      if (fmt) tattn_fwd_kernel<8, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_fwd_kernel<8, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
     default: set_last_error("alpro_temporal_attn_fwd: T=%d unsupported (1,2,4,8)", T); return ALPRO_ENOTSUP;
   }
   ALPRO_CHECK_LAUNCH("alpro_temporal_attn_fwd");
@@ -1035,10 +1066,22 @@ extern "C" int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const vo
   const unsigned grid = static_cast<unsigned>(cdiv(units, wpb));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (T) {
-    case 1: tattn_bwd_kernel<1><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 2: tattn_bwd_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 4: tattn_bwd_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 8: tattn_bwd_kernel<8><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 1:
+      if (fmt) tattn_bwd_kernel<1, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_bwd_kernel<1, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
+    case 2:
+      if (fmt) tattn_bwd_kernel<2, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_bwd_kernel<2, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
+    case 4:
+      if (fmt) tattn_bwd_kernel<4, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_bwd_kernel<4, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
+    case 8:
+      if (fmt) tattn_bwd_kernel<8, true><<<grid, wpb * 32, 0, st>>>(p);
+      else tattn_bwd_kernel<8, false><<<grid, wpb * 32, 0, st>>>(p);
+      break;
     default: set_last_error("alpro_temporal_attn_bwd: T=%d unsupported (1,2,4,8)", T); return ALPRO_ENOTSUP;
   }
   ALPRO_CHECK_LAUNCH("alpro_temporal_attn_bwd");

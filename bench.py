@@ -166,24 +166,41 @@ def run_ours(args):
             p.grad = None
         return out
 
-    def e2e_step():
-        b = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
-        out = step(b)
-        vals = torch.stack([out[k].detach() for k in out if k.endswith("_loss") and out[k] is not None])
-        return vals.cpu()   # D2H read of the step's result (synchronises)
+    # End-to-end step through the public API as a trainer drives it: pinned host batches go through
+    # alpro_b200.prefetch.PrefetchLoader (the reference's PrefetchLoader, src/datasets/dataloader.py:80-157): the H2D
+    # copy of step i+1 runs on a side stream under the kernels of step i. Every timed step issues exactly one batch
+    # copy and reads its losses back to the host.
+    import itertools
+    from alpro_b200.prefetch import PrefetchLoader
+
+    def make_e2e(hb):
+        it = iter(PrefetchLoader(itertools.repeat(hb), device))
+
+        def run():
+            out = step(next(it))
+            vals = torch.stack([out[k].detach() for k in out if k.endswith("_loss") and out[k] is not None])
+            return vals.cpu()   # D2H read of the step's result (synchronises)
+        return run
+
+    e2e_step = make_e2e(host_batch)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    host_ms = {}
+
+    def timed(fn, steps, tag=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        if tag:   # host time to ENQUEUE the steps (launch calls are asynchronous): << device time = not launch-bound
+            host_ms[tag] = (time.perf_counter() - t0) * 1e3 / steps
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
@@ -204,7 +221,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     calls0 = _lib.counted.calls
-    ms_step = timed(lambda: step(dev_batch), args.steps)
+    ms_step = timed(lambda: step(dev_batch), args.steps, tag="step")
     launches = (_lib.counted.calls - calls0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
     e2e_step()
@@ -218,10 +235,7 @@ def run_ours(args):
             host_u8[k] = torch.randint(0, 256, tuple(host_batch[k].shape), dtype=torch.uint8, generator=g8).pin_memory()
     h2d_u8 = batch_bytes(host_u8)
 
-    def e2e_u8_step():
-        b = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_u8.items()}
-        out = step(b)
-        return torch.stack([out[k].detach() for k in out if k.endswith("_loss") and out[k] is not None]).cpu()
+    e2e_u8_step = make_e2e(host_u8)
 
     e2e_u8_step()
     ms_e2e_u8 = timed(e2e_u8_step, args.steps)
@@ -233,7 +247,15 @@ def run_ours(args):
     gemm_ms = sum(e0.elapsed_time(e1) for (_, _, _, e0, e1) in ops.GEMM_PROFILE)
     gemm_flop = sum(2.0 * M * N * K for (M, N, K, _, _) in ops.GEMM_PROFILE)
     n_gemm = len(ops.GEMM_PROFILE)
+    # algorithmic bytes of the same launches: both 16-bit operands once + 2 bytes per output element (lower bound: fp32
+    # outputs / residual reads / the saved GELU derivative add to it)
+    gemm_bytes = sum(2.0 * (M * K + N * K + M * N) for (M, N, K, _, _) in ops.GEMM_PROFILE)
     ops.GEMM_PROFILE = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
     peaks = load_peaks()
     achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
 
@@ -284,18 +306,23 @@ def run_ours(args):
                    "mode": "train (BERT dropout 0.1 hidden+attention, DropPath 0.1 active; teacher in eval)"},
         "tensor_frac_of_peak_whole_step": round(FLOP_PER_PAIR[kind] * value / world / (peaks["sustained"] * 1e12), 4),
         "e2e": {"value": round(pairs / (ms_e2e * 1e-3), 3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 16 if kind == "pretrain" else 8, "ms_per_step": round(ms_e2e, 3)},
+                "d2h_bytes_per_step": 16 if kind == "pretrain" else 8, "ms_per_step": round(ms_e2e, 3),
+                "loader": "alpro_b200.prefetch.PrefetchLoader (pinned host batch, side-stream H2D of the next step)"},
         "e2e_uint8_inputs": {"value": round(pairs / (ms_e2e_u8 * 1e-3), 3), "unit": "pairs/s",
                              "h2d_bytes_per_step": h2d_u8, "ms_per_step": round(ms_e2e_u8, 3)},
         "finite": finite, "losses": loss_vals, "grad_norm": round(gnorm, 5),
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": round(host_ms.get("step", 0.0), 3),
         "ms_per_step_with_fused_adamw": round(ms_opt, 3) if ms_opt else None,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm16_kernel (tcgen05)", "achieved": round(achieved, 1),
                      "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
                      "peak_source": peaks["source"] + " (cuBLAS bf16 sustained)", "launches": n_gemm,
                      "gemm_ms_per_step": round(gemm_ms, 3), "gemm_share_of_step": round(gemm_ms / ms_step, 3),
-                     "traffic": None},
+                     "traffic": traffic.get("traffic_bytes_per_launch") if traffic else None,
+                     "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, profiles/gemm_traffic.json)",
+                     "algorithmic_bytes_per_launch": round(gemm_bytes / max(n_gemm, 1), 1),
+                     "flop_per_launch": round(gemm_flop / max(n_gemm, 1), 1)},
     }
     if world == 1 and not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(kind)

@@ -189,3 +189,24 @@ def test_full_width_shapes_vs_oracle():
             bad.append((n, e))
     print("full-width worst grads", [(n, f"{e:.2e}") for e, n in sorted(errs_g, reverse=True)[:6]])
     assert not bad, bad[:8]
+
+
+def test_prefetch_loader_matches_plain_copies():
+    """alpro_b200.prefetch.PrefetchLoader (reference: src/datasets/dataloader.py:80-157): same batches, same order,
+    tensors on the device, optional normalisation applied to the visual keys only."""
+    from alpro_b200.prefetch import PrefetchLoader
+    g = torch.Generator().manual_seed(5)
+    batches = [{"visual_inputs": torch.randint(0, 256, (2, 2, 3, 8, 8), dtype=torch.uint8, generator=g).pin_memory(),
+                "text_input_ids": torch.randint(0, 100, (2, 6), generator=g).pin_memory(), "type": "video"}
+               for _ in range(4)]
+    got = list(PrefetchLoader(batches))
+    assert len(got) == 4
+    for b, h in zip(got, batches):
+        assert b["type"] == "video" and b["visual_inputs"].is_cuda and b["visual_inputs"].dtype == torch.uint8
+        assert torch.equal(b["visual_inputs"].cpu(), h["visual_inputs"]) and torch.equal(b["text_input_ids"].cpu(), h["text_input_ids"])
+    norm = lambda x: (x - 127.5) / 50.0
+    got = list(PrefetchLoader([("taskA", b) for b in batches], img_normalize=norm))
+    for (task, b), h in zip(got, batches):
+        assert task == "taskA" and b["visual_inputs"].dtype == torch.float32
+        assert torch.allclose(b["visual_inputs"].cpu(), norm(h["visual_inputs"].float()))
+        assert torch.equal(b["text_input_ids"].cpu(), h["text_input_ids"])
