@@ -109,7 +109,8 @@ class _StepFn(torch.autograd.Function):
             raise RuntimeError("backward called on a forward that ran without gradient tracking")
         g = {k: (gi.contiguous().float() if gi is not None else None) for k, gi in zip(ctx.loss_keys, grads)}
         P = model._tensor_dict()
-        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and not n.startswith("prompter.")]
+        c = model._param_cache()
+        named = [(n, p) for n, p in zip(c["names"], c["params"]) if p.requires_grad]
         G = model.engine.backward(P, ctx.ectx, named, g)
         ctx.ectx = None
         out = []
@@ -144,14 +145,37 @@ class AlproBaseModel(nn.Module):
         self._last_out = None
 
     # ---- plumbing
+    # Name -> tensor maps are built once and reused every step (walking named_parameters()/state_dict() cost ~19 ms of
+    # host time per training step, tools/host_profile.py). Parameters keep their identity under .to()/.half()/
+    # load_state_dict (in-place); buffers are re-created by Module._apply, which therefore drops the cache.
+    def _param_cache(self):
+        c = self.__dict__.get("_pcache")
+        if c is None:
+            d = {n: p for n, p in self.named_parameters()}
+            d.update({n: b for n, b in self.named_buffers()})
+            for n, t in list(self.state_dict(keep_vars=True).items()):   # aliases of tied parameters
+                if n not in d:
+                    d[n] = t
+            names, params = [], []
+            for n, p in self.named_parameters():
+                if not n.startswith("prompter."):
+                    names.append(n)
+                    params.append(p)
+            c = {"tensors": d, "names": names, "params": params}
+            self.__dict__["_pcache"] = c
+        return c
+
+    def invalidate_cache(self):
+        """Call after replacing a parameter/buffer OBJECT by hand (in-place updates never need it)."""
+        self.__dict__["_pcache"] = None
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self.invalidate_cache()
+        return out
+
     def _tensor_dict(self):
-        d = {n: p for n, p in self.named_parameters()}
-        d.update({n: b for n, b in self.named_buffers()})
-        # aliases of tied parameters
-        for n, t in list(self.state_dict(keep_vars=True).items()):
-            if n not in d:
-                d[n] = t
-        return d
+        return self._param_cache()["tensors"]
 
     def _check_device(self, batch):
         v = batch["visual_inputs"]
@@ -161,12 +185,8 @@ class AlproBaseModel(nn.Module):
 
     def _run(self, batch):
         self._check_device(batch)
-        names, params = [], []
-        for n, p in self.named_parameters():
-            if n.startswith("prompter."):
-                continue
-            names.append(n)
-            params.append(p)
+        c = self._param_cache()
+        names, params = c["names"], c["params"]
         need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         losses = _StepFn.apply(self, batch, names, need, *params)
         out = dict(self._last_out)
