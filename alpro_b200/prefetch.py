@@ -3,9 +3,12 @@
 Mirrors the reference's PrefetchLoader (src/datasets/dataloader.py:80-157): iterate an inner loader of (pinned) host
 batches, copy the NEXT batch on a dedicated CUDA stream while the current one is consumed, make the compute stream wait
 for that copy before handing the batch out, and record the tensors on the compute stream so the caching allocator does
-not recycle them early. Differences: frames may stay uint8 (alpro_b200 fuses ImageNorm into its patch gather, so the
+not recycle them early. Differences: the copies land in two preallocated device staging sets that are reused
+alternately (no per-step cudaMalloc / allocator traffic on the side stream; the reference's commented-out
+"alternative if record_stream() doesn't work"); frames may stay uint8 (alpro_b200 fuses ImageNorm into its patch gather, so the
 4x smaller uint8 clip is what crosses PCIe); `img_normalize`, when given, is applied on the side stream as in the
-reference (after `.float()`).
+reference (after `.float()`). A batch stays valid until the loader has been advanced twice more (its staging set is
+then overwritten), which is the life time a training step needs.
 """
 import torch
 
@@ -31,6 +34,23 @@ class PrefetchLoader:
         self.img_normalize = img_normalize
         self.stream = torch.cuda.Stream(device=self.device)
         self.batch = None
+        self._ring = [{}, {}]   # two staging sets: path -> device tensor
+        self._slot = 0
+
+    def _stage(self, obj, ring, path=""):
+        """Copy the tensors of `obj` into the staging set `ring` (allocated on first use / shape change)."""
+        if torch.is_tensor(obj):
+            buf = ring.get(path)
+            if buf is None or buf.shape != obj.shape or buf.dtype != obj.dtype:
+                buf = torch.empty(obj.shape, dtype=obj.dtype, device=self.device)
+                ring[path] = buf
+            buf.copy_(obj, non_blocking=True)
+            return buf
+        if isinstance(obj, dict):
+            return {k: self._stage(v, ring, f"{path}/{k}") for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._stage(v, ring, f"{path}/{i}") for i, v in enumerate(obj))
+        return obj
 
     def __len__(self):
         return len(self.loader)
@@ -44,10 +64,14 @@ class PrefetchLoader:
         except StopIteration:
             self.batch = None
             return
+        # the staging set about to be overwritten was handed out two batches ago: the copy may start once the compute
+        # stream has finished what it has been given so far (the consumer has not enqueued the current step yet)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             is_tuple = isinstance(batch, tuple)
             task, body = batch if is_tuple else (None, batch)
-            body = _map(body, lambda t: t.to(self.device, non_blocking=True))
+            body = self._stage(body, self._ring[self._slot])
+            self._slot ^= 1
             if self.img_normalize is not None and isinstance(body, dict):
                 for k in VISUAL_KEYS:
                     if k in body:
@@ -58,7 +82,7 @@ class PrefetchLoader:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_stream(self.stream)
         batch = self.batch
-        if batch is not None:
+        if batch is not None:   # tensors created on the side stream by img_normalize are consumed on the compute stream
             _map(batch[1] if isinstance(batch, tuple) else batch, lambda t: (t.record_stream(cur), t)[1])
         self._preload(it)
         return batch
