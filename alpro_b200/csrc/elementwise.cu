@@ -264,6 +264,175 @@ __global__ void __launch_bounds__(192, 3) layernorm_bwd_kernel(const void* __res
   }
 }
 
+// LayerNorm bwd for large M (the TimeSformer stream: 50k rows x 768): same math and hooks as layernorm_bwd_kernel, built
+// for memory-level parallelism instead of occupancy.
+//   * ONE block of 12 warps per SM; every lane stages ITS OWN 16-byte chunks of the next row's x / dy / dx-accumulate
+//     with cp.async into a private double buffer while it works on the current row (a lane only ever reads what it
+//     copied itself, so cp.async.wait_group is the only synchronisation) -> ~100 KB of loads in flight per SM, where the
+//     register version exposed a DRAM round trip per row (ncu r01i: long-scoreboard bound, 2.6 TB/s);
+//   * dgamma / dbeta / bias-colsum partials live in registers (255 are available at this occupancy): no shared-memory
+//     read-modify-write per element; one block-level reduction + fp32 atomics at the end.
+constexpr int LNB_WARPS = 12;
+template <int NV4>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
+layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long lddy, const float* __restrict__ x,
+                           long long ldx, const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float* __restrict__ gamma, long long M, int d, float* __restrict__ dx32, long long lddx,
+                           int accumulate, uint16_t* __restrict__ dx16, long long lddx16, int fmt, int zero_period,
+                           float* __restrict__ dgamma, float* __restrict__ dbeta, float param_scale,
+                           float* __restrict__ colsum, int colsum_zero_period, const uint16_t* __restrict__ dy_mul16,
+                           long long lddymul, const uint16_t* __restrict__ dx16_mul16, long long lddxmul,
+                           const float* __restrict__ dx16_row_scale, const float* __restrict__ colsum_row_scale) {
+  extern __shared__ __align__(16) uint8_t lnb_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nv = d >> 2;
+  constexpr int ARR = NV4 * 32;                                  // float4 slots per staged row
+  float4* wbase = reinterpret_cast<float4*>(lnb_smem) + static_cast<size_t>(warp) * (2 * 3 * ARR);
+  // stage s: [x | dy | dx]  (dy rows of 16-bit inputs use the first half of their slot array as uint2)
+  auto sx = [&](int s) { return wbase + (s * 3 + 0) * ARR; };
+  auto sdy = [&](int s) { return wbase + (s * 3 + 1) * ARR; };
+  auto sdx = [&](int s) { return wbase + (s * 3 + 2) * ARR; };
+  auto issue = [&](long long row, int s) {
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sx(s) + c)),
+                     "l"(reinterpret_cast<const float4*>(x + row * ldx) + c)
+                     : "memory");
+        if (dy_kind == 0)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdy(s) + c)),
+                       "l"(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * lddy) + c)
+                       : "memory");
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(reinterpret_cast<uint2*>(sdy(s)) + c)),
+                       "l"(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy) + row * lddy) + c)
+                       : "memory");
+        if (accumulate)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdx(s) + c)),
+                       "l"(reinterpret_cast<const float4*>(dx32 + row * lddx) + c)
+                       : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float4 ag[NV4], ab[NV4], ac[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const long long stride = static_cast<long long>(gridDim.x) * LNB_WARPS;
+  long long row = static_cast<long long>(blockIdx.x) * LNB_WARPS + warp;
+  if (row < M) issue(row, 0);
+  int s = 0;
+  for (; row < M; row += stride, s ^= 1) {
+    const long long nrow = row + stride;
+    if (nrow < M) {
+      issue(nrow, s ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float4 xv[NV4], dv[NV4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        xv[i] = sx(s)[c];
+        if (dy_kind == 0) {
+          dv[i] = sdy(s)[c];
+        } else {
+          const uint2 w = reinterpret_cast<const uint2*>(sdy(s))[c];
+          dv[i].x = f16_to_32(static_cast<uint16_t>(w.x & 0xffff), dy_kind - 1);
+          dv[i].y = f16_to_32(static_cast<uint16_t>(w.x >> 16), dy_kind - 1);
+          dv[i].z = f16_to_32(static_cast<uint16_t>(w.y & 0xffff), dy_kind - 1);
+          dv[i].w = f16_to_32(static_cast<uint16_t>(w.y >> 16), dy_kind - 1);
+        }
+        if (dy_mul16) {   // upstream dropout on this LayerNorm's output
+          const uint2 mw = reinterpret_cast<const uint2*>(dy_mul16 + row * lddymul)[c];
+          dv[i].x *= f16_to_32(static_cast<uint16_t>(mw.x & 0xffff), fmt); dv[i].y *= f16_to_32(static_cast<uint16_t>(mw.x >> 16), fmt);
+          dv[i].z *= f16_to_32(static_cast<uint16_t>(mw.y & 0xffff), fmt); dv[i].w *= f16_to_32(static_cast<uint16_t>(mw.y >> 16), fmt);
+        }
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float hx = (xv[i].x - mu) * rs, hy = (xv[i].y - mu) * rs, hz = (xv[i].z - mu) * rs, hw = (xv[i].w - mu) * rs;
+        const float gx = dv[i].x * gm.x, gy = dv[i].y * gm.y, gz = dv[i].z * gm.z, gw = dv[i].w * gm.w;
+        s1 += (gx + gy) + (gz + gw);
+        s2 += (gx * hx + gy * hy) + (gz * hz + gw * hw);
+        ag[i].x += dv[i].x * hx; ag[i].y += dv[i].y * hy; ag[i].z += dv[i].z * hz; ag[i].w += dv[i].w * hw;
+        ab[i].x += dv[i].x; ab[i].y += dv[i].y; ab[i].z += dv[i].z; ab[i].w += dv[i].w;
+      }
+    }
+    const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
+    const bool zero16 = zero_period > 0 && (row % zero_period) == 0;
+    const bool cs_on = colsum != nullptr && !(colsum_zero_period > 0 && (row % colsum_zero_period) == 0);
+    const float cs = colsum_row_scale ? colsum_row_scale[row] : (dx16_row_scale ? dx16_row_scale[row] : 1.f);
+    const float rsv = dx16_row_scale ? dx16_row_scale[row] : 1.f;
+    float4* dxrow = reinterpret_cast<float4*>(dx32 + row * lddx);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        float4 o;
+        o.x = rs * (dv[i].x * gm.x - c1 - (xv[i].x - mu) * rs * c2);
+        o.y = rs * (dv[i].y * gm.y - c1 - (xv[i].y - mu) * rs * c2);
+        o.z = rs * (dv[i].z * gm.z - c1 - (xv[i].z - mu) * rs * c2);
+        o.w = rs * (dv[i].w * gm.w - c1 - (xv[i].w - mu) * rs * c2);
+        if (accumulate) {
+          const float4 pv = sdx(s)[c];
+          o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+        }
+        dxrow[c] = o;
+        if (dx16_mul16) {
+          const uint2 mw = reinterpret_cast<const uint2*>(dx16_mul16 + row * lddxmul)[c];
+          o.x *= f16_to_32(static_cast<uint16_t>(mw.x & 0xffff), fmt); o.y *= f16_to_32(static_cast<uint16_t>(mw.x >> 16), fmt);
+          o.z *= f16_to_32(static_cast<uint16_t>(mw.y & 0xffff), fmt); o.w *= f16_to_32(static_cast<uint16_t>(mw.y >> 16), fmt);
+        }
+        if (cs_on) {
+          ac[i].x += o.x * cs; ac[i].y += o.y * cs; ac[i].z += o.z * cs; ac[i].w += o.w * cs;
+        }
+        if (dx16) {
+          uint2 w;
+          if (zero16) {
+            w.x = w.y = 0u;
+          } else {
+            w.x = pack2_16(o.x * rsv, o.y * rsv, fmt);
+            w.y = pack2_16(o.z * rsv, o.w * rsv, fmt);
+          }
+          reinterpret_cast<uint2*>(dx16 + row * lddx16)[c] = w;
+        }
+      }
+    }
+  }
+  // block reduction of the per-warp register partials through the (now idle) staging memory: red[warp][3][d]
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(lnb_smem);
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      reinterpret_cast<float4*>(red + (warp * 3 + 0) * d)[c] = ag[i];
+      reinterpret_cast<float4*>(red + (warp * 3 + 1) * d)[c] = ab[i];
+      reinterpret_cast<float4*>(red + (warp * 3 + 2) * d)[c] = ac[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f, sc = 0.f;
+    for (int w = 0; w < LNB_WARPS; ++w) {
+      sg += red[(w * 3 + 0) * d + c];
+      sb += red[(w * 3 + 1) * d + c];
+      sc += red[(w * 3 + 2) * d + c];
+    }
+    if (dgamma) atomicAdd(dgamma + c, sg * param_scale);
+    if (dbeta) atomicAdd(dbeta + c, sb * param_scale);
+    if (colsum) atomicAdd(colsum + c, sc * param_scale);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // out[n] += alpha * sum_m x[m,n]   (bias gradients). Each warp streams whole rows slices with 128-bit loads (a warp
 // covers 256 columns of a row), 4 rows in flight; block = 8 warps on different rows, smem reduce, one atomic per column.
@@ -652,12 +821,40 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
   ALPRO_REQUIRE(dy && x && mean && rstd && gamma && dx32 && M > 0, "alpro_layernorm_bwd: bad args");
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_bwd: d=%d unsupported", d);
   ALPRO_REQUIRE(dy_kind >= 0 && dy_kind <= 2, "alpro_layernorm_bwd: dy_kind");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Large row counts (the video token stream): one 12-warp block per SM with cp.async double buffering.
+  // ALPRO_LN_BWD_ASYNC=0 keeps the register/occupancy version (read per call).
+  {
+    const char* e = getenv("ALPRO_LN_BWD_ASYNC");
+    const bool use_async = !(e && e[0] == '0') && M >= 4096 && d <= 768 && aligned16(x) && aligned16(dx32) && (ldx % 4) == 0 &&
+                           (lddx % 4) == 0 && aligned16(dy) && (lddy % 4) == 0;
+    if (use_async) {
+      const int nv4 = d <= 256 ? 2 : 6;
+      const size_t smem_a = static_cast<size_t>(LNB_WARPS) * 2 * 3 * nv4 * 32 * sizeof(float4);
+      int grid_a = static_cast<int>(cdiv(M, LNB_WARPS));
+      if (grid_a > num_sms()) grid_a = num_sms();
+#define ALPRO_LN_BWD_A(NV)                                                                                             \
+  do {                                                                                                                 \
+    cudaFuncSetAttribute(layernorm_bwd_async_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
+                         static_cast<int>(smem_a));                                                                    \
+    layernorm_bwd_async_kernel<NV><<<grid_a, LNB_WARPS * 32, smem_a, st>>>(                                            \
+        dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, accumulate, static_cast<uint16_t*>(dx16),      \
+        lddx16, dx16_fmt, zero_period, dgamma, dbeta, param_scale, colsum, colsum_zero_period,                         \
+        static_cast<const uint16_t*>(dy_mul16), lddymul, static_cast<const uint16_t*>(dx16_mul16), lddxmul,            \
+        dx16_row_scale, colsum_row_scale);                                                                             \
+  } while (0)
+      if (nv4 == 2) ALPRO_LN_BWD_A(2);
+      else ALPRO_LN_BWD_A(6);   // (d > 768 would need 288 KB of staging: stays on the register version)
+#undef ALPRO_LN_BWD_A
+      ALPRO_CHECK_LAUNCH("alpro_layernorm_bwd(async)");
+      return 0;
+    }
+  }
   const int wpb = 6;
   int grid = static_cast<int>(cdiv(M, wpb));
   const int cap = num_sms() * 3;   // one resident wave (3 blocks/SM): fewest same-address atomics at the end
   if (grid > cap) grid = cap;
   const size_t smem = static_cast<size_t>(3) * wpb * d * sizeof(float);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define ALPRO_LN_BWD(NV)                                                                                              \
   do {                                                                                                                \
   cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));  \

@@ -107,10 +107,10 @@ def test_gemm16(case):
 
 
 # ------------------------------------------------------------------------------------------------------------ LN
-@pytest.mark.parametrize("d,eps", [(768, 1e-6), (192, 1e-12)])
-def test_layernorm_fwd_bwd(d, eps):
+@pytest.mark.parametrize("d,eps,M", [(768, 1e-6, 333), (192, 1e-12, 333), (768, 1e-6, 4099), (256, 1e-6, 21000)])
+def test_layernorm_fwd_bwd(d, eps, M):
+    """M >= 4096 takes the cp.async double-buffered backward (one 12-warp block per SM), smaller M the register one."""
     ops = _ops()
-    M = 333
     gen = g(2)
     x = torch.randn(M, d, device=DEV, generator=gen) * 2 + 0.3
     gamma = 1 + 0.1 * torch.randn(d, device=DEV, generator=gen)

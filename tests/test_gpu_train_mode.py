@@ -59,10 +59,11 @@ def test_epilogue_row_scales_and_mask_multiply():
     assert rel(out, (a.float() @ w.float().t() + bias[None]) * mask.float() + resid) < 1e-4
 
 
-def test_layernorm_train_hooks():
+@pytest.mark.parametrize("M", [257, 5003])
+def test_layernorm_train_hooks(M):
     from alpro_b200 import ops
     g = torch.Generator(device=DEV).manual_seed(4)
-    M, d = 257, 768
+    d = 768
     x = torch.randn(M, d, device=DEV, generator=g)
     gamma, beta = 1 + 0.1 * torch.randn(d, device=DEV, generator=g), 0.1 * torch.randn(d, device=DEV, generator=g)
     mask = torch.empty(M, d, device=DEV, dtype=torch.float16)
