@@ -199,14 +199,18 @@ def test_prefetch_loader_matches_plain_copies():
     batches = [{"visual_inputs": torch.randint(0, 256, (2, 2, 3, 8, 8), dtype=torch.uint8, generator=g).pin_memory(),
                 "text_input_ids": torch.randint(0, 100, (2, 6), generator=g).pin_memory(), "type": "video"}
                for _ in range(4)]
-    got = list(PrefetchLoader(batches))
-    assert len(got) == 4
-    for b, h in zip(got, batches):
+    # a batch lives in one of two staging sets and is overwritten two steps later: consume inside the loop
+    n = 0
+    for b, h in zip(PrefetchLoader(batches), batches):
         assert b["type"] == "video" and b["visual_inputs"].is_cuda and b["visual_inputs"].dtype == torch.uint8
         assert torch.equal(b["visual_inputs"].cpu(), h["visual_inputs"]) and torch.equal(b["text_input_ids"].cpu(), h["text_input_ids"])
+        n += 1
+    assert n == 4
     norm = lambda x: (x - 127.5) / 50.0
-    got = list(PrefetchLoader([("taskA", b) for b in batches], img_normalize=norm))
-    for (task, b), h in zip(got, batches):
+    n = 0
+    for (task, b), h in zip(PrefetchLoader([("taskA", b) for b in batches], img_normalize=norm), batches):
         assert task == "taskA" and b["visual_inputs"].dtype == torch.float32
         assert torch.allclose(b["visual_inputs"].cpu(), norm(h["visual_inputs"].float()))
         assert torch.equal(b["text_input_ids"].cpu(), h["text_input_ids"])
+        n += 1
+    assert n == 4
