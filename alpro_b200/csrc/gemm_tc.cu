@@ -486,12 +486,19 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
     } else if (mode == E_RESID_OUT32) {
       tma_epi = tma_epi && !p.out16 && aligned16(p.out32) && (p.ld32 % 4) == 0 && aligned16(p.resid) &&
                 (p.ldresid % 4) == 0;
+    } else if (mode == E_ATOMIC) {   // split-K partial sums: TMA reduce-add instead of red.global per element
+      tma_epi = tma_epi && aligned16(p.out32) && (p.ld32 % 4) == 0;
     } else {
       tma_epi = false;
     }
     if (tma_epi) {
       CUtensorMap tmO, tmO2, tmAux;
-      if (mode == E_RESID_OUT32) {
+      if (mode == E_ATOMIC) {
+        rc = make_map(&tmO, p.out32, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld32, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, 4);
+        if (rc) return rc;
+        tmO2 = tmO;
+        tmAux = tmO;
+      } else if (mode == E_RESID_OUT32) {
         rc = make_map(&tmO, p.out32, (uint64_t)N, (uint64_t)M, (uint64_t)p.ld32, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, 4);
         if (rc) return rc;
         rc = make_map(&tmAux, p.resid, (uint64_t)N, (uint64_t)M, (uint64_t)p.ldresid, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, 4);

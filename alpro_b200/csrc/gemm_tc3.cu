@@ -176,7 +176,8 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_work = p.num_m_tiles * p.num_n_tiles;   // tiles of (2*BM) x BN, one per CTA pair (no split-K here)
+  // work item = (tile of (2*BM) x BN, K split); split_k > 1 only in E_ATOMIC (out32 += partial products)
+  const int num_work = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
@@ -185,9 +186,13 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
-        const int m_blk = w / p.num_n_tiles;
-        const int n_blk = w - m_blk * p.num_n_tiles;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int tile = w / p.split_k;
+        const int split = w - tile * p.split_k;
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile - m_blk * p.num_n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);   // own smem slot free (multicast commit of the leader's MMAs)
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));
           uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
@@ -222,10 +227,13 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const uint32_t a_lbo = p.a_mn ? MN_BOX_BYTES : 16, a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
       const uint32_t b_lbo = p.b_mn ? MN_BOX_BYTES : 16, b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const int split = w % p.split_k;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
@@ -234,7 +242,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-            umma_f16_2cta(tmem_acc, adesc, bdesc, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16_2cta(tmem_acc, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2cta(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -254,13 +262,15 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint64_t* abar = aux_bar + 2 * ew;
     const bool bf = p.out16_fmt != 0;
     constexpr bool LOADS = (MODE == E_GELU_GRAD || MODE == E_RESID_OUT32);   // epilogue input tile via TMA load
-    constexpr int CW = (MODE == E_RESID_OUT32) ? 16 : 32;                    // chunk width: 64-byte rows either way
+    constexpr int CW = (MODE == E_RESID_OUT32 || MODE == E_ATOMIC) ? 16 : 32;   // chunk width: 64-byte rows either way
     constexpr int NCH = 64 / CW;                                             // chunks per warp and tile
     int acc = 0;
     uint32_t acc_phase = 0;
     // chunk (w, ch) of this warp covers columns n_blk*BN + slot*64 + ch*CW .. +CW ; valid while it starts below N
-    auto chunk_col = [&](int w, int ch) { return (w % p.num_n_tiles) * BN + slot * 64 + ch * CW; };
-    auto chunk_row = [&](int w) { return (w / p.num_n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32; };
+    auto chunk_col = [&](int w, int ch) { return ((w / p.split_k) % p.num_n_tiles) * BN + slot * 64 + ch * CW; };
+    auto chunk_row = [&](int w) {
+      return ((w / p.split_k) / p.num_n_tiles) * (2 * BM) + static_cast<int>(cta_rank) * BM + q * 32;
+    };
     // LOADS: cursor of the NEXT chunk whose input tile has to be requested, one chunk ahead of its use
     int pw = cluster_id, pch = 0;
     uint32_t nload = 0, nuse = 0;   // chunks requested / consumed (buffer = n & 1, barrier parity = (n >> 1) & 1)
@@ -285,7 +295,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       RowScale rs;
       rs.ra = p.alpha;
       rs.rb = 1.f;
-      if (MODE != E_GELU_GRAD) {
+      if (MODE != E_GELU_GRAD && MODE != E_ATOMIC) {
         const int row = min(row0 + lane, p.M - 1);
         if (p.rs_acc) {
           const float ra = __ldg(p.rs_acc + row);
@@ -332,6 +342,18 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             else    chunk_math<MODE, false, false>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, b0, rs, pk);
           }
           ++nuse;
+        } else if (MODE == E_ATOMIC) {
+          // split-K partial product: fp32 tile -> staging -> TMA reduce-add into out32 (the L2 performs the adds in
+          // bulk; the per-element red.global of gemm_tc2.cu issued 64 K atomics per tile)
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          b0 = bufp(nuse);
+          ++nuse;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(b0 + stage_off(lane, g)) =
+                make_float4(__uint_as_float(r[4 * g + 0]) * rs.ra, __uint_as_float(r[4 * g + 1]) * rs.ra,
+                            __uint_as_float(r[4 * g + 2]) * rs.ra, __uint_as_float(r[4 * g + 3]) * rs.ra);
         } else {
           if (row_scaled) {
             if (bf) chunk_math<MODE, true, true>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, nullptr, rs, pk);
@@ -361,7 +383,8 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         fence_proxy_async();   // generic-proxy writes of every lane -> visible to the TMA unit
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmO, b0, col0, row0);
+          if (MODE == E_ATOMIC) tma_reduce_add_2d(&tmO, b0, col0, row0);
+          else tma_store_2d(&tmO, b0, col0, row0);
           if (MODE == E_GELU_SAVE && p.out16b) tma_store_2d(&tmO2, bufp(1), col0, row0);
           bulk_commit();
         }
@@ -400,6 +423,7 @@ int launch_2cta_tma_epi(int mode, const CUtensorMap& tmA, const CUtensorMap& tmB
     case E_GELU_SAVE: return launch_mode<E_GELU_SAVE>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
     case E_GELU_GRAD: return launch_mode<E_GELU_GRAD>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
     case E_RESID_OUT32: return launch_mode<E_RESID_OUT32>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
+    case E_ATOMIC: return launch_mode<E_ATOMIC>(tmA, tmB, tmO, tmO2, tmAux, p, grid, st);
     default: return -1;
   }
 }

@@ -65,6 +65,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 2D tiled REDUCTION shared -> global: global[box] += smem[box], performed by the TMA unit / L2 (fp32 add)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared-memory source
 template <int N>

@@ -32,6 +32,8 @@ CASES = {
     "perf_proj_resid": (50208, 768, 768, 0, 0, "f16", "f16", {"bias": 1, "resid": 1, "out32": 1, "perf": 1}),
     "nt_resid_ragged": (1000, 800, 328, 0, 0, "f16", "f16", {"bias": 1, "resid": 1, "skip": 7, "out32": 1}),
     "nt_gelu_nosave": (777, 1024, 256, 0, 0, "bf16", "bf16", {"bias": 1, "act": 1}),
+    "perf_wgrad_sq": (768, 768, 50208, 1, 1, "f16", "f16", {"split": -1, "perf": 1}),
+    "perf_wgrad_fc2": (768, 3072, 50208, 1, 1, "f16", "f16", {"split": -1, "perf": 1}),
     "perf_wgrad": (2304, 768, 50176, 1, 1, "f16", "f16", {"split": -1, "perf": 1}),
     "perf_fc1_gelu": (50208, 3072, 768, 0, 0, "f16", "f16", {"bias": 1, "act": 1, "out16b": 1, "perf": 1}),
     "perf_dgrad": (50176, 768, 2304, 0, 1, "f16", "f16", {"perf": 1}),
