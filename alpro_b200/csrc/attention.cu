@@ -986,6 +986,364 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, tcgen05
+// Same contract as sattn_bwd_kernel with all five contractions on tcgen05 and every probability computed ONCE (the
+// mma.sync kernel recomputes S and dP in two phases: 7 contractions and twice the exponentials).
+//
+// Orientation: the MMA M dimension is the KEY index, so a softmax thread owns one key row j (TMEM lane) and walks over
+// queries; the softmax statistics (lse, D) are per-column broadcasts from shared memory and no row reduction exists:
+//   S^T  = K_kt  Q_c^T   M=128 keys, N<=64 queries, K=64     (A = K tile rows, B = Q rows, both K-major, in place)
+//   dP^T = V_kt dO_c^T   same shapes                         (A = V tile rows, B = dO rows)
+//   P^T  = exp2(S^T*c + mask_j - lse_q),  dS^T = P^T (dP^T - D_q) * scale      -> 16-bit, staged in shared memory as
+//          128B-swizzled [128 keys][64 queries] atoms (thread j writes row j)
+//   dV_kt += P^T  dO_c   M=128 keys, N=64, K=queries of the chunk   (A = staged atom, K-major; B = dO, MN-major in place)
+//   dK_kt += dS^T Q_c    same                                       (A = staged atom;          B = Q,  MN-major in place)
+//   dQ_pair += dS K_kt   M=128 queries (two adjacent atoms), N=64, K=keys of the tile
+//                        (A = the SAME dS^T atoms read MN-major; B = K tile rows, MN-major in place)
+// Steps run over (key tile kt, query chunk c); TMEM (512 columns): two S^T/dP^T stages of 64+64 columns, dV, dK (64+64)
+// for the current key tile, dQ for the two 128-query halves (64+64, accumulated over key tiles).
+// Warp roles: warps 0..7 = softmax/dS (warp w: TMEM lane quarter w%4, column half w/4) and epilogues; warp 8 lane 0 =
+// MMA issuer. The issuer runs one step ahead with S^T/dP^T so the tensor pipe works on step s+1 (and on the gradient
+// MMAs of step s-1) while the softmax warps transform step s.
+// Shared memory: Q, dO [S16][64]; K, V [nkt*128][64] (zero rows beyond S); P^T ring 2 atoms; dS^T 4 atoms (one per query
+// chunk of the current key tile) -> ~215 KB at S=197, one CTA per SM; S <= 240.
+template <bool BF>
+__global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams p) {
+  extern __shared__ uint8_t sm_raw[];
+  const uint32_t raw_addr = smem_u32(sm_raw);
+  uint8_t* sm = sm_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const SeqRows rows = make_rows(p, seq);
+  const int S = p.S;
+  const int S16 = (S + 15) & ~15;      // also the row pitch of the dropout-mask index (shared with the other kernels)
+  const int nkt = (S + 127) >> 7;      // key tiles of 128 rows
+  const int nqc = (S16 + 63) >> 6;     // query chunks of 64
+  const int nsteps = nkt * nqc;
+  const int krows = nkt * 128;
+  uint8_t* sQ = sm;
+  uint8_t* sG = sQ + S16 * 128;        // dO
+  uint8_t* sK = sG + S16 * 128;
+  uint8_t* sV = sK + krows * 128;
+  uint8_t* sP = sV + krows * 128;      // 2 atoms of [128 keys][64 queries]
+  uint8_t* sDS = sP + 2 * 16384;       // 4 atoms (query chunk c of the current key tile)
+  float* sMask = reinterpret_cast<float*>(sDS + 4 * 16384);   // [256] additive key mask * log2(e); -inf beyond S
+  float* sNl = sMask + 256;            // [256] -(base-2 log-sum-exp) of query q; -inf beyond S
+  float* sD = sNl + 256;               // [256] D_q = rowsum(dO_q * O_q)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint64_t* s_full = bars;             // [2] MMA -> softmax: S^T/dP^T stage written
+  uint64_t* s_free = bars + 2;         // [2] softmax -> MMA: stage drained to registers (8 warp arrivals)
+  uint64_t* p_ready = bars + 4;        // [2] softmax -> MMA: P^T / dS^T atoms of the step staged (8 warp arrivals)
+  uint64_t* g_done = bars + 6;         // [2] MMA -> softmax: gradient MMAs of the step retired (staging reusable)
+  uint64_t* acc_full = bars + 8;       //     MMA -> softmax: dV/dK of the key tile complete
+  uint64_t* acc_free = bars + 9;       //     softmax -> MMA: dV/dK read out (8 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int fmt = BF ? 1 : 0;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_free[i], 8);
+        mbar_init(&p_ready[i], 8);
+        mbar_init(&g_done[i], 1);
+      }
+      mbar_init(acc_full, 1);
+      mbar_init(acc_free, 8);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else {
+    // gather the four operand tiles (16-byte cp.async copies, rows beyond S zero-filled through the src-size operand)
+    auto gather = [&](const uint16_t* src, long long ld, int col0, int nrows, uint8_t* tile) {
+      const uint32_t base = smem_u32(tile);
+      for (int idx = tid; idx < nrows * 8; idx += 256) {
+        const int row = idx >> 3, ch = idx & 7;
+        const int rr = row < S ? row : 0;
+        const uint16_t* g = src + rows(rr) * ld + col0 + ch * 8;
+        const uint32_t nbytes = row < S ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + row * 128 + ((ch ^ (row & 7)) << 4)),
+                     "l"(g), "r"(nbytes)
+                     : "memory");
+      }
+    };
+    gather(p.qkv, p.ld_qkv, head * DH, S16, sQ);
+    gather(p.dout, p.ld_o, head * DH, S16, sG);
+    gather(p.qkv, p.ld_qkv, p.d + head * DH, krows, sK);
+    gather(p.qkv, p.ld_qkv, 2 * p.d + head * DH, krows, sV);
+    {
+      const int j = tid;   // 256 gather threads = 256 table entries
+      sMask[j] = j < S ? (p.mask ? p.mask[static_cast<long long>(seq) * S + j] * LOG2E : 0.f) : -INFINITY;
+      sNl[j] = j < S ? -p.lse[(static_cast<long long>(seq) * p.heads + head) * S + j] : -INFINITY;
+    }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+  // token-0 upstream gradient: the group's cls output was the (weighted) mean over the seq_div frames
+  if (p.seq_div > 1 && warp == 0) {
+    const float gscale0 = p.cls_weight ? p.cls_weight[seq] : 1.f / p.seq_div;
+    for (int c = lane; c < 64; c += 32) {
+      uint16_t* e = reinterpret_cast<uint16_t*>(sG + (((c >> 3) ^ 0) << 4) + ((c & 7) << 1));
+      *e = f32_to_16(f16_to_32(*e, fmt) * gscale0, fmt);
+    }
+  }
+  __syncthreads();
+  // D_q = rowsum(dO_q * O_q): O from global (one 128-byte row per warp instruction), dO from the staged tile
+  if (warp < 8) {
+    for (int r0 = warp; r0 < S16; r0 += 64) {
+      uint32_t wo[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + 8 * u;
+        wo[u] = 0u;
+        if (r < S) {
+          const uint16_t* orow = (r == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
+                                                            : p.o_fwd + rows(r) * p.ld_o + head * DH;
+          wo[u] = *reinterpret_cast<const uint32_t*>(orow + lane * 2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + 8 * u;
+        if (r < S16) {   // warp-uniform
+          const int ch = lane >> 2;
+          const uint32_t wg = *reinterpret_cast<const uint32_t*>(sG + r * 128 + ((ch ^ (r & 7)) << 4) + ((lane & 3) << 2));
+          float dsum = f16_to_32(static_cast<uint16_t>(wo[u] & 0xffff), fmt) * f16_to_32(static_cast<uint16_t>(wg & 0xffff), fmt) +
+                       f16_to_32(static_cast<uint16_t>(wo[u] >> 16), fmt) * f16_to_32(static_cast<uint16_t>(wg >> 16), fmt);
+          dsum = warp_sum(dsum);
+          if (lane == 0) sD[r] = dsum;
+        }
+      }
+    }
+  }
+  fence_proxy_async();   // cp.async tiles and the rescaled dO row: generic-proxy writes -> visible to the tensor cores
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t qa = smem_u32(sQ), ga = smem_u32(sG), ka = smem_u32(sK), va = smem_u32(sV);
+      const uint32_t pa = smem_u32(sP), da = smem_u32(sDS);
+      const uint32_t idesc_g = make_idesc_f16(fmt, fmt, 0, 1, 128, DH);   // A staged (K-major), B in place (MN-major)
+      const uint32_t idesc_q = make_idesc_f16(fmt, fmt, 1, 1, 128, DH);   // A = dS^T atoms read MN-major
+      auto issue_sdp = [&](int s) {
+        const int kt = s / nqc, qc = s - kt * nqc, st = s & 1;
+        const int N = min(64, S16 - qc * 64);
+        const uint32_t idesc = make_idesc_f16(fmt, fmt, 0, 0, 128, N);
+        const uint32_t tS = tmem + st * 128, tDP = tS + 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tS, make_smem_desc_sw128(ka + kt * 16384 + ks * 32, 16, 1024),
+                   make_smem_desc_sw128(qa + qc * 8192 + ks * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tDP, make_smem_desc_sw128(va + kt * 16384 + ks * 32, 16, 1024),
+                   make_smem_desc_sw128(ga + qc * 8192 + ks * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+        umma_commit(&s_full[st]);
+      };
+      issue_sdp(0);
+      for (int s = 0; s < nsteps; ++s) {
+        const int kt = s / nqc, qc = s - kt * nqc, st = s & 1;
+        if (s + 1 < nsteps) {
+          if (s + 1 >= 2) {
+            mbar_wait(&s_free[(s + 1) & 1], (((s + 1) >> 1) - 1) & 1);
+            tc_fence_after();
+          }
+          issue_sdp(s + 1);
+        }
+        mbar_wait(&p_ready[st], (s >> 1) & 1);
+        tc_fence_after();
+        if (qc == 0 && kt > 0) {   // dV/dK accumulators of the previous key tile must have been read out
+          mbar_wait(acc_free, (kt - 1) & 1);
+          tc_fence_after();
+        }
+        const int N = min(64, S16 - qc * 64);
+        const int nks = N >> 4;
+        for (int ks = 0; ks < nks; ++ks)   // dV += P^T dO_c
+          umma_f16(tmem + COL_DV, make_smem_desc_sw128(pa + st * 16384 + ks * 32, 16, 1024),
+                   make_smem_desc_sw128(ga + (qc * 64 + ks * 16) * 128, 8192, 1024), idesc_g, (qc > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < nks; ++ks)   // dK += dS^T Q_c
+          umma_f16(tmem + COL_DK, make_smem_desc_sw128(da + qc * 16384 + ks * 32, 16, 1024),
+                   make_smem_desc_sw128(qa + (qc * 64 + ks * 16) * 128, 8192, 1024), idesc_g, (qc > 0 || ks > 0) ? 1u : 0u);
+        if ((qc & 1) || qc == nqc - 1) {   // dQ[128-query half] += dS K_kt  (both atoms of the half are staged)
+          const int pair = qc >> 1;
+          const int nkk = min(8, (S - kt * 128 + 15) >> 4);
+          for (int ks = 0; ks < nkk; ++ks)
+            umma_f16(tmem + COL_DQ + pair * 64, make_smem_desc_sw128(da + pair * 32768 + ks * 2048, 16384, 1024),
+                     make_smem_desc_sw128(ka + (kt * 128 + ks * 16) * 128, 8192, 1024), idesc_q, (kt > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&g_done[st]);
+        if (qc == nqc - 1) umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------------------------- softmax / dS warps
+    const int lq = warp & 3, grp = warp >> 2;
+    const int rloc = lq * 32 + lane;                                   // key row inside the tile = TMEM lane
+    const uint32_t tlane = tmem + (static_cast<uint32_t>(lq * 32) << 16);
+    const float sl2 = p.scale * LOG2E;
+    const int fbase = (static_cast<int>(p.dcls_qkv != nullptr));      // token 0 goes to the fp32 cls scratch
+    for (int s = 0; s < nsteps; ++s) {
+      const int kt = s / nqc, qc = s - kt * nqc, st = s & 1;
+      const int N = min(64, S16 - qc * 64);
+      const int j = kt * 128 + rloc;                                   // key index of this thread
+      const float mk = sMask[j];
+      mbar_wait(&s_full[st], (s >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[2][16], dv[2][16];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int sc = grp * 2 + u;                                    // 16-query sub-chunk of the 64-query chunk
+        if (sc * 16 < N) {                                             // warp-uniform
+          tmem_ld_32x16(tlane + st * 128 + sc * 16, sv[u]);
+          tmem_ld_32x16(tlane + st * 128 + 64 + sc * 16, dv[u]);
+        }
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[st]);
+      if (s >= 2) mbar_wait(&g_done[st], ((s >> 1) - 1) & 1);          // staging of step s-2 (and older) consumed
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int sc = grp * 2 + u;
+        if (sc * 16 < N) {
+          const int q0 = qc * 64 + sc * 16;
+          float pv[16], ds[16];
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 nl = *reinterpret_cast<const float4*>(sNl + q0 + e4 * 4);
+            const float4 dd = *reinterpret_cast<const float4*>(sD + q0 + e4 * 4);
+            const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, ddv[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = e4 * 4 + e;
+              float pe = ex2(fmaf(__uint_as_float(sv[u][i]), sl2, nlv[e]) + mk);
+              float dp = __uint_as_float(dv[u][i]);
+              if (p.drop_thr) {   // dP flows through the dropout mask of the forward pass; dV uses the dropped P
+                float lo, hi;
+                drop_pair(p, S16, seq, head, q0 + i, j >> 1, lo, hi);
+                const float mq = (j & 1) ? hi : lo;
+                dp *= mq;
+                ds[i] = pe * (dp - ddv[e]) * p.scale;
+                pe *= mq;
+              } else {
+                ds[i] = pe * (dp - ddv[e]) * p.scale;
+              }
+              pv[i] = pe;
+            }
+          }
+          uint8_t* prow = sP + st * 16384 + rloc * 128;
+          uint8_t* drow = sDS + qc * 16384 + rloc * 128;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 w, x;
+            w.x = pack2<BF>(pv[h * 8 + 0], pv[h * 8 + 1]); w.y = pack2<BF>(pv[h * 8 + 2], pv[h * 8 + 3]);
+            w.z = pack2<BF>(pv[h * 8 + 4], pv[h * 8 + 5]); w.w = pack2<BF>(pv[h * 8 + 6], pv[h * 8 + 7]);
+            x.x = pack2<BF>(ds[h * 8 + 0], ds[h * 8 + 1]); x.y = pack2<BF>(ds[h * 8 + 2], ds[h * 8 + 3]);
+            x.z = pack2<BF>(ds[h * 8 + 4], ds[h * 8 + 5]); x.w = pack2<BF>(ds[h * 8 + 6], ds[h * 8 + 7]);
+            const int off = ((sc * 2 + h) ^ (rloc & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + off) = w;
+            *reinterpret_cast<uint4*>(drow + off) = x;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[st]);
+
+      if (qc == nqc - 1) {
+        // ---- key tile finished: dV (warps 0-3) / dK (warps 4-7) rows of this tile -> global
+        mbar_wait(acc_full, kt & 1);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        const uint32_t tacc = tlane + (grp == 0 ? COL_DV : COL_DK);
+        tmem_ld_32x32(tacc, r0);
+        tmem_ld_32x32(tacc + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        if (j < S) {
+          const int coff = (grp == 0 ? 2 * p.d : p.d) + head * DH;
+          if (j == 0 && fbase) {
+            float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + coff;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              dst[c] = __uint_as_float(r0[c]);
+              dst[32 + c] = __uint_as_float(r1[c]);
+            }
+          } else {
+            uint16_t* dst = p.dqkv + rows(j) * p.ld_qkv + coff;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint4 w, x;
+              w.x = pack2<BF>(__uint_as_float(r0[q4 * 8 + 0]), __uint_as_float(r0[q4 * 8 + 1]));
+              w.y = pack2<BF>(__uint_as_float(r0[q4 * 8 + 2]), __uint_as_float(r0[q4 * 8 + 3]));
+              w.z = pack2<BF>(__uint_as_float(r0[q4 * 8 + 4]), __uint_as_float(r0[q4 * 8 + 5]));
+              w.w = pack2<BF>(__uint_as_float(r0[q4 * 8 + 6]), __uint_as_float(r0[q4 * 8 + 7]));
+              x.x = pack2<BF>(__uint_as_float(r1[q4 * 8 + 0]), __uint_as_float(r1[q4 * 8 + 1]));
+              x.y = pack2<BF>(__uint_as_float(r1[q4 * 8 + 2]), __uint_as_float(r1[q4 * 8 + 3]));
+              x.z = pack2<BF>(__uint_as_float(r1[q4 * 8 + 4]), __uint_as_float(r1[q4 * 8 + 5]));
+              x.w = pack2<BF>(__uint_as_float(r1[q4 * 8 + 6]), __uint_as_float(r1[q4 * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + q4 * 8) = w;
+              *reinterpret_cast<uint4*>(dst + 32 + q4 * 8) = x;
+            }
+          }
+        }
+      }
+    }
+    // ---- dQ: every MMA has retired (acc_full of the last key tile was committed after the last dQ MMA)
+    if (grp * 128 < S) {   // warp-uniform
+      const int i = grp * 128 + rloc;
+      uint32_t r0[32], r1[32];
+      const uint32_t tacc = tlane + COL_DQ + grp * 64;
+      tmem_ld_32x32(tacc, r0);
+      tmem_ld_32x32(tacc + 32, r1);
+      tmem_ld_wait();
+      if (i < S) {
+        if (i == 0 && fbase) {
+          float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + head * DH;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            dst[c] = __uint_as_float(r0[c]);
+            dst[32 + c] = __uint_as_float(r1[c]);
+          }
+        } else {
+          uint16_t* dst = p.dqkv + rows(i) * p.ld_qkv + head * DH;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 w, x;
+            w.x = pack2<BF>(__uint_as_float(r0[q4 * 8 + 0]), __uint_as_float(r0[q4 * 8 + 1]));
+            w.y = pack2<BF>(__uint_as_float(r0[q4 * 8 + 2]), __uint_as_float(r0[q4 * 8 + 3]));
+            w.z = pack2<BF>(__uint_as_float(r0[q4 * 8 + 4]), __uint_as_float(r0[q4 * 8 + 5]));
+            w.w = pack2<BF>(__uint_as_float(r0[q4 * 8 + 6]), __uint_as_float(r0[q4 * 8 + 7]));
+            x.x = pack2<BF>(__uint_as_float(r1[q4 * 8 + 0]), __uint_as_float(r1[q4 * 8 + 1]));
+            x.y = pack2<BF>(__uint_as_float(r1[q4 * 8 + 2]), __uint_as_float(r1[q4 * 8 + 3]));
+            x.z = pack2<BF>(__uint_as_float(r1[q4 * 8 + 4]), __uint_as_float(r1[q4 * 8 + 5]));
+            x.w = pack2<BF>(__uint_as_float(r1[q4 * 8 + 6]), __uint_as_float(r1[q4 * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + q4 * 8) = w;
+            *reinterpret_cast<uint4*>(dst + 32 + q4 * 8) = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // dqkv[group cls row] = sum over the group's seq_div frames of the per-sequence cls-row gradients
 __global__ void cls_qkv_reduce_kernel(const float* __restrict__ part, uint16_t* __restrict__ dqkv, long long ld,
                                       long long clip_rows, int groups, int seq_div, int d3, int fmt) {
@@ -1174,7 +1532,23 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   const size_t smem = static_cast<size_t>(S_pad) * 128 * 4 + 3 * S_pad * sizeof(float);
   dim3 grid(heads, nseq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (fmt == 1) {
+  const char* tc_env = getenv("ALPRO_ATTN_BWD_TC");   // read per call so tests can switch implementations
+  const bool use_tc = tc_env && tc_env[0] == '1' && S <= 240;
+  if (use_tc) {   // tcgen05 / TMEM backward: same inputs, outputs and dropout stream as the mma.sync kernel
+    const size_t krows = static_cast<size_t>((S + 127) / 128) * 128;
+    const size_t smem_tc = 1024 + 2 * static_cast<size_t>(S_pad) * 128 + 2 * krows * 128 + 6 * 16384 +
+                           3 * 256 * sizeof(float) + 10 * sizeof(uint64_t) + 16;
+    if (fmt == 1) {
+      rc = set_smem(sattn_bwd_tc_kernel<true>, smem_tc);
+      if (rc) return rc;
+      sattn_bwd_tc_kernel<true><<<grid, 288, smem_tc, st>>>(p);
+    } else {
+      rc = set_smem(sattn_bwd_tc_kernel<false>, smem_tc);
+      if (rc) return rc;
+      sattn_bwd_tc_kernel<false><<<grid, 288, smem_tc, st>>>(p);
+    }
+    ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd(tcgen05)");
+  } else if (fmt == 1) {
     rc = set_smem(sattn_bwd_kernel<true>, smem);
     if (rc) return rc;
     sattn_bwd_kernel<true><<<grid, 256, smem, st>>>(p);
