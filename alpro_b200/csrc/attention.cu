@@ -1532,9 +1532,13 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   const size_t smem = static_cast<size_t>(S_pad) * 128 * 4 + 3 * S_pad * sizeof(float);
   dim3 grid(heads, nseq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* tc_env = getenv("ALPRO_ATTN_BWD_TC");   // read per call so tests can switch implementations
-  const bool use_tc = tc_env && tc_env[0] == '1' && S <= 240;
-  if (use_tc) {   // tcgen05 / TMEM backward: same inputs, outputs and dropout stream as the mma.sync kernel
+  // tcgen05 / TMEM backward (default for 96 <= S <= 240: 0.58 vs 0.75 ms at 256x12 sequences of 197, 0.44 vs 0.81 ms at
+  // 128x12 of 237 with dropout; the per-CTA fixed cost makes it slower than mma.sync for short text sequences).
+  // ALPRO_ATTN_BWD_TC=0 forces the mma.sync kernel, =1 forces tcgen05 wherever it fits (S <= 240); read per call so
+  // tests can switch implementations.
+  const char* tc_env = getenv("ALPRO_ATTN_BWD_TC");
+  const bool use_tc = S <= 240 && (tc_env && (tc_env[0] == '0' || tc_env[0] == '1') ? tc_env[0] == '1' : S >= 96);
+  if (use_tc) {   // same inputs, outputs and dropout stream as the mma.sync kernel
     const size_t krows = static_cast<size_t>((S + 127) / 128) * 128;
     const size_t smem_tc = 1024 + 2 * static_cast<size_t>(S_pad) * 128 + 2 * krows * 128 + 6 * 16384 +
                            3 * 256 * sizeof(float) + 10 * sizeof(uint64_t) + 16;

@@ -289,9 +289,8 @@ def test_temporal_attention(T):
     assert rel(gotd[:, 1:], want) < 3e-3 and float(gotd[:, 0].abs().max()) == 0.0
 
 
-# "tcgen05_bwd" (the TMEM backward kernel) joins the default matrix once it has been confirmed on a B200; until then it
-# runs only under ALPRO_TEST_EXPERIMENTAL=1 so that an unverified kernel cannot turn the GPU suite red.
-_ATTN_IMPLS = ["mma_sync", "tcgen05"] + (["tcgen05_bwd"] if os.environ.get("ALPRO_TEST_EXPERIMENTAL") == "1" else [])
+# forward: mma.sync (default) / tcgen05 (ALPRO_ATTN_TC=1); backward: mma.sync / tcgen05 (default for 96 <= S <= 240)
+_ATTN_IMPLS = ["mma_sync", "tcgen05", "tcgen05_bwd"]
 
 
 @pytest.fixture(params=_ATTN_IMPLS)
