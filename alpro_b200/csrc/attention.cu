@@ -337,6 +337,7 @@ struct SAttnParams {
   // train-mode attention-probability dropout (BertSelfAttention.dropout, xbert.py:331): 0 = off
   uint32_t drop_thr, drop_seed;
   float drop_scale;
+  long long* trace;      // diagnostics (ALPRO_ATTN_TRACE=1): 64 clock64() stamps per CTA, null in normal runs
 };
 
 // mask/keep factors of the key pair (2*jp, 2*jp+1) for query row i of (seq, head): one counter-hash per pair
@@ -1007,8 +1008,14 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
 // MMAs of step s-1) while the softmax warps transform step s.
 // Shared memory: Q, dO [S16][64]; K, V [nkt*128][64] (zero rows beyond S); P^T ring 2 atoms; dS^T 4 atoms (one per query
 // chunk of the current key tile) -> ~215 KB at S=197, one CTA per SM; S <= 240.
-template <bool BF>
+#define ATTN_TRACE(cond, slot)                                                                             \
+  do {                                                                                                   \
+    if (p.trace && (cond))                                                                               \
+      p.trace[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64() - t_start; \
+  } while (0)
+template <bool BF, bool DROP>
 __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams p) {
+  const long long t_start = p.trace ? clock64() : 0;
   extern __shared__ uint8_t sm_raw[];
   const uint32_t raw_addr = smem_u32(sm_raw);
   uint8_t* sm = sm_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -1028,7 +1035,7 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
   uint8_t* sDS = sP + 2 * 16384;       // 4 atoms (query chunk c of the current key tile)
   float* sMask = reinterpret_cast<float*>(sDS + 4 * 16384);   // [256] additive key mask * log2(e); -inf beyond S
   float* sNl = sMask + 256;            // [256] -(base-2 log-sum-exp) of query q; -inf beyond S
-  float* sD = sNl + 256;               // [256] D_q = rowsum(dO_q * O_q)
+  float* sD = sNl + 256;               // [256] scale * D_q, D_q = rowsum(dO_q * O_q)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
   uint64_t* s_full = bars;             // [2] MMA -> softmax: S^T/dP^T stage written
   uint64_t* s_free = bars + 2;         // [2] softmax -> MMA: stage drained to registers (8 warp arrivals)
@@ -1037,7 +1044,8 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
   uint64_t* acc_full = bars + 8;       //     MMA -> softmax: dV/dK of the key tile complete
   uint64_t* acc_free = bars + 9;       //     softmax -> MMA: dV/dK read out (8 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role branches stay uniform
   constexpr int fmt = BF ? 1 : 0;
 
   if (warp == 8) {
@@ -1056,16 +1064,19 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   } else {
-    // gather the four operand tiles (16-byte cp.async copies, rows beyond S zero-filled through the src-size operand)
+    // Thread t owns the 16-byte chunk ch = t & 7 of rows (t >> 3) + 32 u of every tile. ALL global reads of the unit
+    // (four gathered tiles, the O rows for D, mask / lse tables) are issued before the first wait: one DRAM round trip.
+    const int ch = tid & 7, r0 = tid >> 3;
+    const uint32_t swz = static_cast<uint32_t>((ch ^ (r0 & 7)) << 4);   // (row & 7) == (r0 & 7): rows advance by 32
     auto gather = [&](const uint16_t* src, long long ld, int col0, int nrows, uint8_t* tile) {
-      const uint32_t base = smem_u32(tile);
-      for (int idx = tid; idx < nrows * 8; idx += 256) {
-        const int row = idx >> 3, ch = idx & 7;
-        const int rr = row < S ? row : 0;
-        const uint16_t* g = src + rows(rr) * ld + col0 + ch * 8;
-        const uint32_t nbytes = row < S ? 16u : 0u;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + row * 128 + ((ch ^ (row & 7)) << 4)),
-                     "l"(g), "r"(nbytes)
+      const uint32_t dst = smem_u32(tile) + r0 * 128 + swz;
+      const uint16_t* g0 = src + rows(r0 < S ? r0 : 0) * ld + col0 + ch * 8;
+      const uint16_t* g1 = src + rows(r0 + 32) * ld + col0 + ch * 8;     // only dereferenced when r0 + 32 < S
+      const long long step = 32LL * rows.stride * ld;
+      for (int u = 0, row = r0; row < nrows; ++u, row += 32) {
+        const bool valid = row < S;                                      // rows beyond S: zero-fill (src-size 0)
+        const uint16_t* g = (u == 0 || !valid) ? g0 : g1 + (u - 1) * step;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + u * 4096), "l"(g), "r"(valid ? 16u : 0u)
                      : "memory");
       }
     };
@@ -1073,48 +1084,54 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
     gather(p.dout, p.ld_o, head * DH, S16, sG);
     gather(p.qkv, p.ld_qkv, p.d + head * DH, krows, sK);
     gather(p.qkv, p.ld_qkv, 2 * p.d + head * DH, krows, sV);
+    uint4 ov[8];   // this thread's chunks of the forward outputs O (for D_q = rowsum(dO_q * O_q))
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = r0 + 32 * u;
+      ov[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < S) {
+        const uint16_t* orow = (row == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
+                                                            : p.o_fwd + rows(row) * p.ld_o + head * DH;
+        ov[u] = *reinterpret_cast<const uint4*>(orow + ch * 8);
+      }
+    }
     {
       const int j = tid;   // 256 gather threads = 256 table entries
       sMask[j] = j < S ? (p.mask ? p.mask[static_cast<long long>(seq) * S + j] * LOG2E : 0.f) : -INFINITY;
       sNl[j] = j < S ? -p.lse[(static_cast<long long>(seq) * p.heads + head) * S + j] : -INFINITY;
     }
+    ATTN_TRACE(tid == 0, 1);
     cp_async_wait_all();
-  }
-  __syncthreads();
-  // token-0 upstream gradient: the group's cls output was the (weighted) mean over the seq_div frames
-  if (p.seq_div > 1 && warp == 0) {
-    const float gscale0 = p.cls_weight ? p.cls_weight[seq] : 1.f / p.seq_div;
-    for (int c = lane; c < 64; c += 32) {
-      uint16_t* e = reinterpret_cast<uint16_t*>(sG + (((c >> 3) ^ 0) << 4) + ((c & 7) << 1));
-      *e = f32_to_16(f16_to_32(*e, fmt) * gscale0, fmt);
-    }
-  }
-  __syncthreads();
-  // D_q = rowsum(dO_q * O_q): O from global (one 128-byte row per warp instruction), dO from the staged tile
-  if (warp < 8) {
-    for (int r0 = warp; r0 < S16; r0 += 64) {
-      uint32_t wo[8];
+    ATTN_TRACE(tid == 0, 2);
+    // D from this thread's own chunks of dO (cp.async data of the issuing thread is visible after the wait). The
+    // token-0 upstream gradient is rescaled in place first: the group's cls output was the (weighted) mean over frames.
+    const float gscale0 = p.seq_div > 1 ? (p.cls_weight ? p.cls_weight[seq] : 1.f / p.seq_div) : 1.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = r0 + 8 * u;
-        wo[u] = 0u;
-        if (r < S) {
-          const uint16_t* orow = (r == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
-                                                            : p.o_fwd + rows(r) * p.ld_o + head * DH;
-          wo[u] = *reinterpret_cast<const uint32_t*>(orow + lane * 2);
-        }
-      }
+    for (int u = 0; u < 8; ++u) {
+      const int row = r0 + 32 * u;
+      if (row < S16) {   // warp-uniform (a warp covers 4 consecutive rows, S16 is a multiple of 16)
+        uint4* gp = reinterpret_cast<uint4*>(sG + row * 128 + swz);
+        uint4 gv = *gp;
+        uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        const uint32_t ow[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w};
+        float dsum = 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = r0 + 8 * u;
-        if (r < S16) {   // warp-uniform
-          const int ch = lane >> 2;
-          const uint32_t wg = *reinterpret_cast<const uint32_t*>(sG + r * 128 + ((ch ^ (r & 7)) << 4) + ((lane & 3) << 2));
-          float dsum = f16_to_32(static_cast<uint16_t>(wo[u] & 0xffff), fmt) * f16_to_32(static_cast<uint16_t>(wg & 0xffff), fmt) +
-                       f16_to_32(static_cast<uint16_t>(wo[u] >> 16), fmt) * f16_to_32(static_cast<uint16_t>(wg >> 16), fmt);
-          dsum = warp_sum(dsum);
-          if (lane == 0) sD[r] = dsum;
+        for (int k = 0; k < 4; ++k) {
+          float g0f, g1f, o0f, o1f;
+          unpack2<BF>(gw[k], g0f, g1f);
+          unpack2<BF>(ow[k], o0f, o1f);
+          if (row == 0 && p.seq_div > 1) {
+            gw[k] = pack2c<BF>(g0f * gscale0, g1f * gscale0);
+            unpack2<BF>(gw[k], g0f, g1f);
+          }
+          dsum = fmaf(g0f, o0f, dsum);
+          dsum = fmaf(g1f, o1f, dsum);
         }
+        if (row == 0 && p.seq_div > 1) *gp = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
+        if (ch == 0) sD[row] = dsum * p.scale;   // pre-scaled: dS = P * (dP * scale - D * scale)
       }
     }
   }
@@ -1124,47 +1141,55 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+  ATTN_TRACE(tid == 0, 3);
 
   if (warp == 8) {
     // ---------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the (uniform) loop and waits on the barriers; one elected lane issues.
+    {
       const uint32_t qa = smem_u32(sQ), ga = smem_u32(sG), ka = smem_u32(sK), va = smem_u32(sV);
       const uint32_t pa = smem_u32(sP), da = smem_u32(sDS);
       const uint32_t idesc_g = make_idesc_f16(fmt, fmt, 0, 1, 128, DH);   // A staged (K-major), B in place (MN-major)
       const uint32_t idesc_q = make_idesc_f16(fmt, fmt, 1, 1, 128, DH);   // A = dS^T atoms read MN-major
-      auto issue_sdp = [&](int s) {
-        const int kt = s / nqc, qc = s - kt * nqc, st = s & 1;
+      auto issue_sdp = [&](int s, int kt, int qc) {
+        const int st = s & 1;
         const int N = min(64, S16 - qc * 64);
         const uint32_t idesc = make_idesc_f16(fmt, fmt, 0, 0, 128, N);
         const uint32_t tS = tmem + st * 128, tDP = tS + 64;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tS, make_smem_desc_sw128(ka + kt * 16384 + ks * 32, 16, 1024),
-                   make_smem_desc_sw128(qa + qc * 8192 + ks * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tS, make_smem_desc_sw128(ka + kt * 16384 + ks * 32, 16, 1024),
+                     make_smem_desc_sw128(qa + qc * 8192 + ks * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tDP, make_smem_desc_sw128(va + kt * 16384 + ks * 32, 16, 1024),
-                   make_smem_desc_sw128(ga + qc * 8192 + ks * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
-        umma_commit(&s_full[st]);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tDP, make_smem_desc_sw128(va + kt * 16384 + ks * 32, 16, 1024),
+                     make_smem_desc_sw128(ga + qc * 8192 + ks * 32, 16, 1024), idesc, ks > 0 ? 1u : 0u);
+          umma_commit(&s_full[st]);
+        }
+        __syncwarp();
       };
-      issue_sdp(0);
-      for (int s = 0; s < nsteps; ++s) {
-        const int kt = s / nqc, qc = s - kt * nqc, st = s & 1;
+      issue_sdp(0, 0, 0);
+      for (int s = 0, kt = 0, qc = 0; s < nsteps; ++s) {
+        const int st = s & 1;
+        const int qn = qc + 1 == nqc ? 0 : qc + 1, ktn = qc + 1 == nqc ? kt + 1 : kt;   // step s + 1
         if (s + 1 < nsteps) {
           if (s + 1 >= 2) {
             mbar_wait(&s_free[(s + 1) & 1], (((s + 1) >> 1) - 1) & 1);
             tc_fence_after();
           }
-          issue_sdp(s + 1);
+          issue_sdp(s + 1, ktn, qn);
         }
         mbar_wait(&p_ready[st], (s >> 1) & 1);
         tc_fence_after();
+        ATTN_TRACE(lane == 0 && s < 8, 48 + 2 * s);
         if (qc == 0 && kt > 0) {   // dV/dK accumulators of the previous key tile must have been read out
           mbar_wait(acc_free, (kt - 1) & 1);
           tc_fence_after();
         }
         const int N = min(64, S16 - qc * 64);
         const int nks = N >> 4;
+        if (elect_one()) {
         for (int ks = 0; ks < nks; ++ks)   // dV += P^T dO_c
           umma_f16(tmem + COL_DV, make_smem_desc_sw128(pa + st * 16384 + ks * 32, 16, 1024),
                    make_smem_desc_sw128(ga + (qc * 64 + ks * 16) * 128, 8192, 1024), idesc_g, (qc > 0 || ks > 0) ? 1u : 0u);
@@ -1180,6 +1205,11 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
         }
         umma_commit(&g_done[st]);
         if (qc == nqc - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+        ATTN_TRACE(lane == 0 && s < 8, 49 + 2 * s);
+        qc = qn;
+        kt = ktn;
       }
     }
   } else {
@@ -1189,13 +1219,74 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
     const uint32_t tlane = tmem + (static_cast<uint32_t>(lq * 32) << 16);
     const float sl2 = p.scale * LOG2E;
     const int fbase = (static_cast<int>(p.dcls_qkv != nullptr));      // token 0 goes to the fp32 cls scratch
-    for (int s = 0; s < nsteps; ++s) {
-      const int kt = s / nqc, qc = s - kt * nqc, st = s & 1;
+    // One 32-row x 64-column fp32 accumulator block of this warp: TMEM -> 16-bit -> this warp's 4 KB staging block
+    // (swizzled) -> global with 8 lanes per 128-byte row (4 full lines per store instruction; a lane storing its own
+    // row touched 32 lines per instruction and the LSU serialised them: 2-4K cycles per read-out, trace r01p).
+    // Token 0 of the shared-cls layout goes to the fp32 scratch straight from the registers.
+    auto store_block = [&](uint32_t tacc, uint8_t* stg, int jbase, int coff, uint64_t* release) {
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tacc, r0);
+      tmem_ld_32x32(tacc + 32, r1);
+      tmem_ld_wait();
+      if (release) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release);
+      }
+      if (jbase + lane == 0 && fbase) {
+        float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + coff;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          dst[c] = __uint_as_float(r0[c]);
+          dst[32 + c] = __uint_as_float(r1[c]);
+        }
+      }
+      uint8_t* myrow = stg + lane * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 w, x;
+        w.x = pack2<BF>(__uint_as_float(r0[q4 * 8 + 0]), __uint_as_float(r0[q4 * 8 + 1]));
+        w.y = pack2<BF>(__uint_as_float(r0[q4 * 8 + 2]), __uint_as_float(r0[q4 * 8 + 3]));
+        w.z = pack2<BF>(__uint_as_float(r0[q4 * 8 + 4]), __uint_as_float(r0[q4 * 8 + 5]));
+        w.w = pack2<BF>(__uint_as_float(r0[q4 * 8 + 6]), __uint_as_float(r0[q4 * 8 + 7]));
+        x.x = pack2<BF>(__uint_as_float(r1[q4 * 8 + 0]), __uint_as_float(r1[q4 * 8 + 1]));
+        x.y = pack2<BF>(__uint_as_float(r1[q4 * 8 + 2]), __uint_as_float(r1[q4 * 8 + 3]));
+        x.z = pack2<BF>(__uint_as_float(r1[q4 * 8 + 4]), __uint_as_float(r1[q4 * 8 + 5]));
+        x.w = pack2<BF>(__uint_as_float(r1[q4 * 8 + 6]), __uint_as_float(r1[q4 * 8 + 7]));
+        *reinterpret_cast<uint4*>(myrow + ((q4 ^ (lane & 7)) << 4)) = w;
+        *reinterpret_cast<uint4*>(myrow + (((4 + q4) ^ (lane & 7)) << 4)) = x;
+      }
+      __syncwarp();
+      const int c = lane & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const int jj = jbase + rr;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((c ^ (rr & 7)) << 4));
+        if (jj < S && !(jj == 0 && fbase))
+          *reinterpret_cast<uint4*>(p.dqkv + rows(jj) * p.ld_qkv + coff + c * 8) = v;
+      }
+      __syncwarp();
+    };
+    // dV (warps 0-3) / dK (warps 4-7) rows of key tile k. Staging: rows [0,128) of the V / K tiles, which no MMA reads
+    // any more when this runs (tile 0 is read out during tile 1; the last tile after every MMA has retired).
+    auto store_dkv = [&](int k) {
+      ATTN_TRACE(tid == 0, 36 + 3 * (k & 1));
+      mbar_wait(acc_full, k & 1);
+      tc_fence_after();
+      ATTN_TRACE(tid == 0, 37 + 3 * (k & 1));
+      store_block(tlane + (grp == 0 ? COL_DV : COL_DK), (grp == 0 ? sV : sK) + lq * 4096, k * 128 + lq * 32,
+                  (grp == 0 ? 2 * p.d : p.d) + head * DH, acc_free);
+      ATTN_TRACE(tid == 0, 38 + 3 * (k & 1));
+    };
+    for (int s = 0, kt = 0, qc = 0; s < nsteps; ++s) {
+      const int st = s & 1;
       const int N = min(64, S16 - qc * 64);
       const int j = kt * 128 + rloc;                                   // key index of this thread
       const float mk = sMask[j];
       mbar_wait(&s_full[st], (s >> 1) & 1);
       tc_fence_after();
+      ATTN_TRACE(tid == 0 && s < 8, 4 + 4 * s);
       uint32_t sv[2][16], dv[2][16];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -1209,7 +1300,9 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[st]);
+      ATTN_TRACE(tid == 0 && s < 8, 5 + 4 * s);
       if (s >= 2) mbar_wait(&g_done[st], ((s >> 1) - 1) & 1);          // staging of step s-2 (and older) consumed
+      ATTN_TRACE(tid == 0 && s < 8, 6 + 4 * s);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int sc = grp * 2 + u;
@@ -1226,15 +1319,14 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
               const int i = e4 * 4 + e;
               float pe = ex2(fmaf(__uint_as_float(sv[u][i]), sl2, nlv[e]) + mk);
               float dp = __uint_as_float(dv[u][i]);
-              if (p.drop_thr) {   // dP flows through the dropout mask of the forward pass; dV uses the dropped P
+              if (DROP) {   // dP flows through the dropout mask of the forward pass; dV uses the dropped P
                 float lo, hi;
                 drop_pair(p, S16, seq, head, q0 + i, j >> 1, lo, hi);
                 const float mq = (j & 1) ? hi : lo;
-                dp *= mq;
-                ds[i] = pe * (dp - ddv[e]) * p.scale;
+                ds[i] = pe * fmaf(dp * mq, p.scale, -ddv[e]);
                 pe *= mq;
               } else {
-                ds[i] = pe * (dp - ddv[e]) * p.scale;
+                ds[i] = pe * fmaf(dp, p.scale, -ddv[e]);
               }
               pv[i] = pe;
             }
@@ -1257,92 +1349,33 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[st]);
+      ATTN_TRACE(tid == 0 && s < 8, 7 + 4 * s);
 
-      if (qc == nqc - 1) {
-        // ---- key tile finished: dV (warps 0-3) / dK (warps 4-7) rows of this tile -> global
-        mbar_wait(acc_full, kt & 1);
-        tc_fence_after();
-        uint32_t r0[32], r1[32];
-        const uint32_t tacc = tlane + (grp == 0 ? COL_DV : COL_DK);
-        tmem_ld_32x32(tacc, r0);
-        tmem_ld_32x32(tacc + 32, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_free);
-        if (j < S) {
-          const int coff = (grp == 0 ? 2 * p.d : p.d) + head * DH;
-          if (j == 0 && fbase) {
-            float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + coff;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              dst[c] = __uint_as_float(r0[c]);
-              dst[32 + c] = __uint_as_float(r1[c]);
-            }
-          } else {
-            uint16_t* dst = p.dqkv + rows(j) * p.ld_qkv + coff;
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint4 w, x;
-              w.x = pack2<BF>(__uint_as_float(r0[q4 * 8 + 0]), __uint_as_float(r0[q4 * 8 + 1]));
-              w.y = pack2<BF>(__uint_as_float(r0[q4 * 8 + 2]), __uint_as_float(r0[q4 * 8 + 3]));
-              w.z = pack2<BF>(__uint_as_float(r0[q4 * 8 + 4]), __uint_as_float(r0[q4 * 8 + 5]));
-              w.w = pack2<BF>(__uint_as_float(r0[q4 * 8 + 6]), __uint_as_float(r0[q4 * 8 + 7]));
-              x.x = pack2<BF>(__uint_as_float(r1[q4 * 8 + 0]), __uint_as_float(r1[q4 * 8 + 1]));
-              x.y = pack2<BF>(__uint_as_float(r1[q4 * 8 + 2]), __uint_as_float(r1[q4 * 8 + 3]));
-              x.z = pack2<BF>(__uint_as_float(r1[q4 * 8 + 4]), __uint_as_float(r1[q4 * 8 + 5]));
-              x.w = pack2<BF>(__uint_as_float(r1[q4 * 8 + 6]), __uint_as_float(r1[q4 * 8 + 7]));
-              *reinterpret_cast<uint4*>(dst + q4 * 8) = w;
-              *reinterpret_cast<uint4*>(dst + 32 + q4 * 8) = x;
-            }
-          }
-        }
+      // The read-out of the previous key tile's dV/dK is deferred until this tile's first chunk has been transformed:
+      // the tensor pipe finishes the last gradient MMAs of tile kt-1 meanwhile and the issuer already has work queued.
+      if (qc == 0 && kt > 0) store_dkv(kt - 1);
+      if (++qc == nqc) {
+        qc = 0;
+        ++kt;
       }
     }
-    // ---- dQ: every MMA has retired (acc_full of the last key tile was committed after the last dQ MMA)
-    if (grp * 128 < S) {   // warp-uniform
-      const int i = grp * 128 + rloc;
-      uint32_t r0[32], r1[32];
-      const uint32_t tacc = tlane + COL_DQ + grp * 64;
-      tmem_ld_32x32(tacc, r0);
-      tmem_ld_32x32(tacc + 32, r1);
-      tmem_ld_wait();
-      if (i < S) {
-        if (i == 0 && fbase) {
-          float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + head * DH;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            dst[c] = __uint_as_float(r0[c]);
-            dst[32 + c] = __uint_as_float(r1[c]);
-          }
-        } else {
-          uint16_t* dst = p.dqkv + rows(i) * p.ld_qkv + head * DH;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 w, x;
-            w.x = pack2<BF>(__uint_as_float(r0[q4 * 8 + 0]), __uint_as_float(r0[q4 * 8 + 1]));
-            w.y = pack2<BF>(__uint_as_float(r0[q4 * 8 + 2]), __uint_as_float(r0[q4 * 8 + 3]));
-            w.z = pack2<BF>(__uint_as_float(r0[q4 * 8 + 4]), __uint_as_float(r0[q4 * 8 + 5]));
-            w.w = pack2<BF>(__uint_as_float(r0[q4 * 8 + 6]), __uint_as_float(r0[q4 * 8 + 7]));
-            x.x = pack2<BF>(__uint_as_float(r1[q4 * 8 + 0]), __uint_as_float(r1[q4 * 8 + 1]));
-            x.y = pack2<BF>(__uint_as_float(r1[q4 * 8 + 2]), __uint_as_float(r1[q4 * 8 + 3]));
-            x.z = pack2<BF>(__uint_as_float(r1[q4 * 8 + 4]), __uint_as_float(r1[q4 * 8 + 5]));
-            x.w = pack2<BF>(__uint_as_float(r1[q4 * 8 + 6]), __uint_as_float(r1[q4 * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + q4 * 8) = w;
-            *reinterpret_cast<uint4*>(dst + 32 + q4 * 8) = x;
-          }
-        }
-      }
-    }
+    store_dkv(nkt - 1);
+    // ---- dQ: every MMA has retired (acc_full of the last key tile was committed after the last dQ MMA); staging in
+    // the P^T ring
+    if (grp * 128 < S)   // warp-uniform
+      store_block(tlane + COL_DQ + grp * 64, sP + grp * 16384 + lq * 4096, grp * 128 + lq * 32, head * DH, nullptr);
   }
+  ATTN_TRACE(tid == 0, 42);
   tc_fence_before();
   __syncthreads();
+  ATTN_TRACE(tid == 0, 43);
   if (warp == 8) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
 }
+#undef ATTN_TRACE
 
 // dqkv[group cls row] = sum over the group's seq_div frames of the per-sequence cls-row gradients
 __global__ void cls_qkv_reduce_kernel(const float* __restrict__ part, uint16_t* __restrict__ dqkv, long long ld,
@@ -1446,6 +1479,21 @@ extern "C" int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const vo
   return 0;
 }
 
+static long long* g_trace = nullptr;   // ALPRO_ATTN_TRACE=1 diagnostics buffer (64 stamps per CTA of the last traced launch)
+static size_t g_trace_len = 0;
+
+extern "C" int alpro_debug_attn_trace(void* host_out, int64_t max_values) {
+  ALPRO_REQUIRE(host_out && max_values > 0, "alpro_debug_attn_trace: bad args");
+  if (!g_trace) return 0;
+  const size_t n = g_trace_len < static_cast<size_t>(max_values) ? g_trace_len : static_cast<size_t>(max_values);
+  cudaError_t e = cudaMemcpy(host_out, g_trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    set_last_error("alpro_debug_attn_trace: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return static_cast<int>(n / 64);
+}
+
 static int fill_sattn(SAttnParams& p, const void* qkv, int64_t ld_qkv, const float* mask, int S, int nseq, int heads,
                       int fmt, int seq_div, int stride, int64_t clip_rows, float scale, float drop_p,
                       uint32_t drop_seed) {
@@ -1539,18 +1587,35 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   const char* tc_env = getenv("ALPRO_ATTN_BWD_TC");
   const bool use_tc = S <= 240 && (tc_env && (tc_env[0] == '0' || tc_env[0] == '1') ? tc_env[0] == '1' : S >= 96);
   if (use_tc) {   // same inputs, outputs and dropout stream as the mma.sync kernel
+    const char* tr_env = getenv("ALPRO_ATTN_TRACE");
+    if (tr_env && tr_env[0] == '1') {   // diagnostics only: per-CTA phase stamps, read back by alpro_debug_attn_trace
+      const size_t need = static_cast<size_t>(heads) * nseq * 64;
+      if (need > g_trace_len) {
+        if (g_trace) cudaFree(g_trace);
+        g_trace = nullptr;
+        g_trace_len = 0;
+        if (cudaMalloc(&g_trace, need * sizeof(long long)) == cudaSuccess) g_trace_len = need;
+      }
+      if (g_trace) {
+        cudaMemsetAsync(g_trace, 0, g_trace_len * sizeof(long long), st);
+        p.trace = g_trace;
+      }
+    }
     const size_t krows = static_cast<size_t>((S + 127) / 128) * 128;
     const size_t smem_tc = 1024 + 2 * static_cast<size_t>(S_pad) * 128 + 2 * krows * 128 + 6 * 16384 +
                            3 * 256 * sizeof(float) + 10 * sizeof(uint64_t) + 16;
+#define LAUNCH_BWD_TC(BF, DR)                                          \
+  do {                                                                 \
+    rc = set_smem(sattn_bwd_tc_kernel<BF, DR>, smem_tc);               \
+    if (rc) return rc;                                                 \
+    sattn_bwd_tc_kernel<BF, DR><<<grid, 288, smem_tc, st>>>(p);        \
+  } while (0)
     if (fmt == 1) {
-      rc = set_smem(sattn_bwd_tc_kernel<true>, smem_tc);
-      if (rc) return rc;
-      sattn_bwd_tc_kernel<true><<<grid, 288, smem_tc, st>>>(p);
+      if (p.drop_thr) LAUNCH_BWD_TC(true, true); else LAUNCH_BWD_TC(true, false);
     } else {
-      rc = set_smem(sattn_bwd_tc_kernel<false>, smem_tc);
-      if (rc) return rc;
-      sattn_bwd_tc_kernel<false><<<grid, 288, smem_tc, st>>>(p);
+      if (p.drop_thr) LAUNCH_BWD_TC(false, true); else LAUNCH_BWD_TC(false, false);
     }
+#undef LAUNCH_BWD_TC
     ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd(tcgen05)");
   } else if (fmt == 1) {
     rc = set_smem(sattn_bwd_kernel<true>, smem);

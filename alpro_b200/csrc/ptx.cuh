@@ -98,6 +98,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of the (fully converged) warp. Issuing tcgen05.mma / commit under `if (elect_one())` inside WARP-UNIFORM
+// control flow lets nvcc keep descriptors in uniform registers and emit back-to-back UTCHMMA; issuing them under a
+// `lane == 0` branch makes it wrap every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~100 cycles per MMA:
+// invisible behind 128-cycle GEMM MMAs, dominant for the 32-cycle MMAs of the attention kernels).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16 and bf16 operands with fp32 accumulate.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {

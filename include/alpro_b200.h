@@ -170,6 +170,12 @@ int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* mask, const
 /* test utility: materialises the mask/keep factors [nseq, heads, S, S] the two functions above apply for (drop_p, seed) */
 int alpro_attn_dropout_mask(float* out, int S, int nseq, int heads, float drop_p, uint32_t drop_seed, void* stream);
 
+/* Diagnostics (no reference counterpart): with ALPRO_ATTN_TRACE=1 in the environment the tcgen05 backward kernel
+ * records 64 clock64() stamps per CTA (phase boundaries relative to CTA start). Copies the stamps of the last traced
+ * launch to host_out (int64 values, synchronises the device); returns the number of CTAs copied, 0 if nothing was
+ * traced, -1 on error. tools/check_attn_tc.py --cases trace:vit prints the per-phase medians. */
+int alpro_debug_attn_trace(void* host_out, int64_t max_values);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Task-head kernels, fp32 (alpro_b200/csrc/heads.cu)
  */

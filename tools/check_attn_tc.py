@@ -194,6 +194,36 @@ def run_time(which):
     return res
 
 
+SLOTS = {1: "loads issued", 2: "cp.async landed", 3: "prologue done"}
+for _s in range(8):
+    SLOTS[4 + 4 * _s] = f"s{_s} S/dP ready"
+    SLOTS[5 + 4 * _s] = f"s{_s} tmem drained"
+    SLOTS[6 + 4 * _s] = f"s{_s} staging free"
+    SLOTS[7 + 4 * _s] = f"s{_s} P/dS staged"
+    SLOTS[48 + 2 * _s] = f"  mma: s{_s} p_ready seen"
+    SLOTS[49 + 2 * _s] = f"  mma: s{_s} grads issued"
+SLOTS.update({36: "dkv0 wait", 37: "dkv0 acc_full", 38: "dkv0 stored", 39: "dkv1 wait", 40: "dkv1 acc_full",
+              41: "dkv1 stored", 42: "dq stored", 43: "cta done"})
+
+
+def run_trace(which):
+    """Per-phase timeline of the tcgen05 backward kernel (median over CTAs of the clock64 stamps, in cycles)."""
+    import ctypes
+    import torch
+    os.environ["ALPRO_ATTN_TRACE"] = "1"
+    res = run_time(which)
+    from alpro_b200 import _lib
+    n = 12 * 256 * 64
+    buf = (ctypes.c_int64 * n)()
+    nct = _lib.lib.alpro_debug_attn_trace(ctypes.cast(buf, ctypes.c_void_p), n)
+    t = torch.tensor(list(buf[: nct * 64]), dtype=torch.float64).view(nct, 64)
+    med = t.median(0).values
+    order = sorted((float(med[k]), k) for k in SLOTS if float(med[k]) > 0)
+    res["timeline"] = [f"{int(v):6d} {SLOTS[k]}" for v, k in order]
+    res["ctas"] = nct
+    return res
+
+
 def run_case(case):
     parts = case.split(":")
     if parts[0] == "bert":
@@ -202,6 +232,8 @@ def run_case(case):
         return run_vit(int(parts[1]), int(parts[2]))
     if parts[0] == "time":
         return run_time(parts[1])
+    if parts[0] == "trace":
+        return run_trace(parts[1])
     raise SystemExit("unknown case " + case)
 
 
