@@ -146,7 +146,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint64_t* aux_bar = tempty_bar + 2;       // [NUM_EPI_WARPS][2] TMA load of the saved-derivative tile -> epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * NUM_EPI_WARPS);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform role branches)
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();   // 0 = leader (issues the MMAs), 1 = peer
 
@@ -182,7 +182,8 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // the whole warp walks the loop (uniform control flow); one elected lane issues the TMA instructions
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
@@ -194,32 +195,36 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);   // own smem slot free (multicast commit of the leader's MMAs)
-          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));
-          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
-          uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
-          const int m0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM;
-          const int n0 = n_blk * BN + static_cast<int>(cta_rank) * BNH;
-          if (!p.a_mn) {
-            tma_load_2d_2cta(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
-          } else {
+          if (elect_one()) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));
+            uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+            uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+            const int m0 = m_blk * (2 * BM) + static_cast<int>(cta_rank) * BM;
+            const int n0 = n_blk * BN + static_cast<int>(cta_rank) * BNH;
+            if (!p.a_mn) {
+              tma_load_2d_2cta(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d_2cta(a_dst + j * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
-          }
-          if (!p.b_mn) {
-            tma_load_2d_2cta(b_dst, &tmB, &full_bar[stage], kb * BK, n0);
-          } else {
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d_2cta(a_dst + j * MN_BOX_BYTES, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_2cta(b_dst, &tmB, &full_bar[stage], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BNH / 64; ++j)
-              tma_load_2d_2cta(b_dst + j * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+              for (int j = 0; j < BNH / 64; ++j)
+                tma_load_2d_2cta(b_dst + j * MN_BOX_BYTES, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread of the leader CTA)
-    if (lane == 0 && cta_rank == 0) {
+    // the leader CTA's whole warp walks the loop; one elected lane issues MMAs and commits (see elect_one, ptx.cuh)
+    if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -238,16 +243,20 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-            umma_f16_2cta(tmem_acc, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+              umma_f16_2cta(tmem_acc, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty_bar[stage]);
           }
-          umma_commit_2cta(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(&tfull_bar[acc]);
+        if (elect_one()) umma_commit_2cta(&tfull_bar[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
