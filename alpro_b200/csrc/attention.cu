@@ -804,30 +804,47 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
 
 // ------------------------------------------------------------------------------------------------ forward, tcgen05
 // Same contract as sattn_fwd_kernel, but both contractions run on the 5th-generation tensor cores:
-//   S = Q K^T : tcgen05.mma M=128, N=S_pad (<= 256), K=64   -> fp32 scores in TMEM (one TMEM lane per query row)
+//   S = Q K^T : tcgen05.mma M=128, N=S32 (<= 256), K=64   -> fp32 scores in TMEM (one TMEM lane per query row)
 //   softmax   : thread r owns query row r (tcgen05.ld of its TMEM lane), base-2 exp, fp32 row statistics
 //   O = P V   : P written as a 16-bit K-major 128B-swizzled A tile in shared memory (128 keys at a time),
 //               V consumed in place as an MN-major B operand; fp32 O accumulator in TMEM columns [0,64)
 // The gathered Q/K/V tiles already use the UMMA 128B-swizzle K-major layout, so the cp.async gather needs no repacking.
-// One CTA (4 warps) per (sequence, head), <= ~100 KB smem and 256 TMEM columns -> two CTAs per SM overlap each other's
+// One CTA (4 warps) per (sequence, head), ~105 KB smem and 256 TMEM columns -> two CTAs per SM overlap each other's
 // load / MMA / softmax phases. 197 queries = two M=128 tiles (the second has 69 valid rows).
-template <bool BF>
-__global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) {
+// r01p revision (lessons of the backward kernel's phase trace): MMAs issued by an elected lane in warp-uniform control
+// flow (back-to-back UTCHMMA instead of one ELECT/R2UR loop per MMA), the next query tile is gathered while the current
+// one is processed, TMEM chunks are loaded two at a time, O rows leave through a swizzled staging block so that every
+// store instruction writes four full 128-byte rows, dropout is a template parameter.
+#define ATTN_TRACE(cond, slot)                                                                             \
+  do {                                                                                                   \
+    if (p.trace && (cond))                                                                               \
+      p.trace[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64() - t_start; \
+  } while (0)
+template <bool BF, bool DROP, bool MASK>
+__global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams p) {
+  const long long t_start = p.trace ? clock64() : 0;
   extern __shared__ uint8_t sm_raw[];
   const uint32_t raw_addr = smem_u32(sm_raw);
   uint8_t* sm = sm_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int head = blockIdx.x, seq = blockIdx.y;
   const SeqRows rows = make_rows(p, seq);
-  const int S_pad = (p.S + 15) & ~15;  // dropout-mask indexing (shared with the mma.sync kernels)
-  const int S32 = (p.S + 31) & ~31;    // keys padded to whole 32-column TMEM chunks; padded K/V rows are zero
+  const int S = p.S;
+  const int S_pad = (S + 15) & ~15;  // dropout-mask indexing (shared with the mma.sync kernels)
+  const int S32 = (S + 31) & ~31;    // keys padded to whole 32-column TMEM chunks; padded K/V rows are zero
   uint8_t* sQ = sm;                    // [128][64]  one query tile
   uint8_t* sK = sQ + 128 * 128;        // [S32][64]
   uint8_t* sV = sK + S32 * 128;        // [S32][64]
-  uint8_t* sP = sV + S32 * 128;        // 2 blocks of [128][64]: probabilities of 128 keys
+  uint8_t* sP = sV + S32 * 128;        // 2 blocks of [128][64]: probabilities of 128 keys; O staging in the epilogue
   float* sMask = reinterpret_cast<float*>(sP + 2 * 16384);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sMask + 256);
+  float* sStat = sMask + 256;          // [2][128] row maxima, then [2][128] row sums of the two column halves
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sStat + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+  // Two threads per query row: warp w and warp w + 4 share TMEM lane quarter w % 4; group `wg` takes the 32-key chunks
+  // with (chunk & 1) == wg, and columns [32 wg, 32 wg + 32) of the output row.
+  const int wg = warp >> 2, lq = warp & 3;
+  const int rit = lq * 32 + lane;      // row inside the query tile = TMEM lane
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -838,80 +855,131 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
-  load_tile(p, p.qkv, p.ld_qkv, p.d + head * DH, rows, S32, sK, nullptr);
-  load_tile(p, p.qkv, p.ld_qkv, 2 * p.d + head * DH, rows, S32, sV, nullptr);
-  for (int j = tid; j < 256; j += 128)
-    sMask[j] = j < p.S ? (p.mask ? p.mask[static_cast<long long>(seq) * p.S + j] * LOG2E : 0.f) : -INFINITY;
+  // thread t owns the 16-byte chunk ch = t & 7 of rows (t >> 3) + 32 u of every tile
+  const int ch = tid & 7, r0 = tid >> 3;
+  const uint32_t swz = static_cast<uint32_t>((ch ^ (r0 & 7)) << 4);   // (row & 7) == (r0 & 7): rows advance by 32
+  // rows [row_lo, row_lo + nrows) of the sequence -> tile rows [0, nrows); rows beyond S are zero-filled
+  // (token j >= 1 lives at canonical row first + (j-1) * stride: one pointer increment per copy; the 64-bit
+  // row(j) * ld products of the first version were 22% of the kernel's instructions, ncu r01p)
+  auto gather = [&](int col0, int row_lo, int nrows, uint8_t* tile) {
+    const uint32_t dst = smem_u32(tile) + r0 * 128 + swz;
+    const uint16_t* src = p.qkv + col0 + ch * 8;
+    const uint16_t* tok0 = src + rows.base * p.ld_qkv;
+    const uint16_t* g = src + (rows.first + static_cast<long long>(row_lo + r0 - 1) * rows.stride) * p.ld_qkv;
+    const long long step = 32LL * rows.stride * p.ld_qkv;
+    for (int u = 0, gr = row_lo + r0; u * 32 + r0 < nrows; ++u, gr += 32, g += step) {
+      const bool valid = gr < S;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + u * 4096),
+                   "l"((gr == 0 || !valid) ? tok0 : g), "r"(valid ? 16u : 0u)
+                   : "memory");
+    }
+  };
+  gather(p.d + head * DH, 0, S32, sK);
+  gather(head * DH, 0, 128, sQ);
+  gather(2 * p.d + head * DH, 0, S32, sV);
+  sMask[tid] = tid < S ? (p.mask ? p.mask[static_cast<long long>(seq) * S + tid] * LOG2E : 0.f) : -INFINITY;
+  ATTN_TRACE(tid == 0, 1);
+  cp_async_wait_all();
+  fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  ATTN_TRACE(tid == 0, 2);
   const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);   // this warp's TMEM lane quarter
+  const uint32_t trow = tmem + (static_cast<uint32_t>(lq * 32) << 16);   // this warp's TMEM lane quarter
   const float sl2 = p.scale * LOG2E;
-  const int fmt = BF ? 1 : 0;
+  constexpr int fmt = BF ? 1 : 0;
   const uint32_t idesc_s = make_idesc_f16(fmt, fmt, 0, 0, 128, S32);
   const uint32_t idesc_o = make_idesc_f16(fmt, fmt, 0, 1, 128, DH);
   const int nks = S32 >> 4;            // 16-key steps of the PV contraction
   const int nchunk = S32 >> 5;
+  const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), pa = smem_u32(sP);
   uint32_t phase = 0;
 
-  for (int qt = 0; qt * 128 < p.S; ++qt) {
-    // ---- stage this query tile (rows beyond S are zero-filled), first tile also waits for K / V
-    {
-      const uint32_t base = smem_u32(sQ);
-      for (int idx = tid; idx < 128 * 8; idx += 128) {
-        const int row = idx >> 3, ch = idx & 7;
-        const int gr = qt * 128 + row;
-        const int rr = gr < p.S ? gr : 0;
-        const uint16_t* g = p.qkv + rows(rr) * p.ld_qkv + head * DH + ch * 8;
-        const uint32_t nbytes = gr < p.S ? 16u : 0u;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + row * 128 + ((ch ^ (row & 7)) << 4)),
-                     "l"(g), "r"(nbytes)
-                     : "memory");
-      }
-    }
-    cp_async_wait_all();
-    fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+  for (int qt = 0; qt * 128 < S; ++qt) {
+    if (warp == 0) {   // uniform branch; one elected lane issues
+      if (elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_f16(tmem, make_smem_desc_sw128(qa + ks * 32, 16, 1024), make_smem_desc_sw128(ka + ks * 32, 16, 1024),
-                 idesc_s, ks > 0 ? 1u : 0u);
-      umma_commit(bar);
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tmem, make_smem_desc_sw128(qa + ks * 32, 16, 1024), make_smem_desc_sw128(ka + ks * 32, 16, 1024),
+                   idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
+    ATTN_TRACE(tid == 0 && qt < 2, 4 + 10 * qt);
+    const bool more = (qt + 1) * 128 < S;
+    if (more) gather(head * DH, (qt + 1) * 128, 128, sQ);   // sQ is free again: next query tile lands under the softmax
 
-    const int row = qt * 128 + tid;    // query row owned by this thread
-    __syncwarp();                      // lane 0 of warp 0 took the MMA-issue branch: reconverge before tcgen05.ld
-    // ---- pass 1: row maximum (base-2 domain)
-    float m = -INFINITY;
-    for (int c = 0; c < nchunk; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(trow + c * 32, r);
-      tmem_ld_wait();
+    const int row = qt * 128 + rit;    // query row owned by this thread (shared with its partner in the other group)
+    // ---- pass 1: maximum over this thread's chunks (base-2 domain, 4 independent chains), then over both groups
+    float m;
+    {
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      for (int c = wg; c < nchunk; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c * 32, r);
+        tmem_ld_wait();
+        if (MASK || (c + 1) * 32 > S) {   // additive mask, or the chunk that holds the padded keys (mask = -inf)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), sl2, sMask[c * 32 + j]));
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 mk = *reinterpret_cast<const float4*>(sMask + c * 32 + j4 * 4);
+            m0 = fmaxf(m0, fmaf(__uint_as_float(r[j4 * 4 + 0]), sl2, mk.x));
+            m1 = fmaxf(m1, fmaf(__uint_as_float(r[j4 * 4 + 1]), sl2, mk.y));
+            m2 = fmaxf(m2, fmaf(__uint_as_float(r[j4 * 4 + 2]), sl2, mk.z));
+            m3 = fmaxf(m3, fmaf(__uint_as_float(r[j4 * 4 + 3]), sl2, mk.w));
+          }
+        } else {                          // no mask: maximum of the raw scores, scaled once (sl2 > 0)
+          float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            x0 = fmaxf(x0, __uint_as_float(r[j4 * 4 + 0]));
+            x1 = fmaxf(x1, __uint_as_float(r[j4 * 4 + 1]));
+            x2 = fmaxf(x2, __uint_as_float(r[j4 * 4 + 2]));
+            x3 = fmaxf(x3, __uint_as_float(r[j4 * 4 + 3]));
+          }
+          m0 = fmaxf(m0, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)) * sl2);
+        }
+      }
+      m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      sStat[wg * 128 + rit] = m;
+      __syncthreads();
+      m = fmaxf(m, sStat[(wg ^ 1) * 128 + rit]);   // token 0 is never masked: the row maximum is finite
     }
+    ATTN_TRACE(tid == 0 && qt < 2, 5 + 10 * qt);
     // ---- pass 2: probabilities, 128 keys at a time -> sP -> O (+)= P V
-    float l = 0.f;
+    float l0 = 0.f, l1 = 0.f;
     for (int half = 0; half * 128 < S32; ++half) {
       const int c0 = half * 4, c1 = min(nchunk, c0 + 4);
-      for (int c = c0; c < c1; ++c) {
+      for (int c = c0 + wg; c < c1; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
         float pv[32];
+        if (MASK || (c + 1) * 32 > S) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          pv[j] = ex2(fmaf(__uint_as_float(r[j]), sl2, sMask[c * 32 + j]) - m);   // keys >= S: mask = -inf -> 0
-          l += pv[j];
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 mk = *reinterpret_cast<const float4*>(sMask + c * 32 + j4 * 4);
+            const float mkv[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e;
+              pv[j] = ex2(fmaf(__uint_as_float(r[j]), sl2, mkv[e]) - m);   // keys >= S: mask = -inf -> 0
+              if (e & 1) l1 += pv[j]; else l0 += pv[j];
+            }
+          }
+        } else {
+          const float nm = -m;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            pv[j] = ex2(fmaf(__uint_as_float(r[j]), sl2, nm));
+            if (j & 1) l1 += pv[j]; else l0 += pv[j];
+          }
         }
-        if (p.drop_thr) {
+        if (DROP) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a0, a1;
@@ -921,68 +989,84 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
           }
         }
         // 32 keys = 4 chunks of 16 bytes in block (c - c0) / 2 of this half
-        uint8_t* blk = sP + ((c - c0) >> 1) * 16384 + tid * 128;
+        uint8_t* blk = sP + ((c - c0) >> 1) * 16384 + rit * 128;
         const int cb0 = ((c - c0) & 1) * 4;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint4 w;
           w.x = pack2<BF>(pv[q4 * 8 + 0], pv[q4 * 8 + 1]); w.y = pack2<BF>(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
           w.z = pack2<BF>(pv[q4 * 8 + 4], pv[q4 * 8 + 5]); w.w = pack2<BF>(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
-          *reinterpret_cast<uint4*>(blk + (((cb0 + q4) ^ (tid & 7)) << 4)) = w;
+          *reinterpret_cast<uint4*>(blk + (((cb0 + q4) ^ (rit & 7)) << 4)) = w;
         }
       }
+      sStat[256 + wg * 128 + rit] = l0 + l1;   // running partial row sum (complete after the last half)
+      ATTN_TRACE(tid == 0 && qt < 2 && half < 2, 6 + 10 * qt + 2 * half);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
-        const int k0 = half * 8, k1 = min(nks, k0 + 8);
-        for (int ks = k0; ks < k1; ++ks) {
-          const int kl = ks - k0;
-          umma_f16(tmem, make_smem_desc_sw128(pa + (kl >> 2) * 16384 + (kl & 3) * 32, 16, 1024),
-                   make_smem_desc_sw128(va + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
+        if (elect_one()) {
+          const int k0 = half * 8, k1 = min(nks, k0 + 8);
+          for (int ks = k0; ks < k1; ++ks) {
+            const int kl = ks - k0;
+            umma_f16(tmem, make_smem_desc_sw128(pa + (kl >> 2) * 16384 + (kl & 3) * 32, 16, 1024),
+                     make_smem_desc_sw128(va + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(bar);
         }
-        umma_commit(bar);
+        __syncwarp();
       }
       mbar_wait(bar, phase);           // sP may be overwritten / O may be read after this
       phase ^= 1;
       tc_fence_after();
-      __syncwarp();
+      ATTN_TRACE(tid == 0 && qt < 2 && half < 2, 7 + 10 * qt + 2 * half);
     }
-    // ---- epilogue: O row / l -> 16-bit, log-sum-exp for the backward. tcgen05.ld is warp-collective (.sync.aligned):
-    // every lane executes the loads, only lanes that own a real query row store.
+    // ---- epilogue: this thread's 32 columns of its O row / l -> 16-bit -> staging rows in sP block 0 (the PV MMAs have
+    // retired) -> global with 8 lanes per 128-byte row; log-sum-exp for the backward.
     {
-      const bool valid = row < p.S;
-      const int rr = valid ? row : 0;
+      const float l = sStat[256 + rit] + sStat[256 + 128 + rit];
       const float inv = 1.f / l;
-      uint16_t* dst = (rr == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
-                                           : p.o + rows(rr) * p.ld_o + head * DH;
-      __syncwarp();
+      uint32_t r[32];
+      tmem_ld_32x32(trow + wg * 32, r);
+      tmem_ld_wait();
+      uint8_t* myrow = sP + rit * 128;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + c * 32, r);
-        tmem_ld_wait();
-        if (valid) {
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 w;
+        w.x = pack2<BF>(__uint_as_float(r[q4 * 8 + 0]) * inv, __uint_as_float(r[q4 * 8 + 1]) * inv);
+        w.y = pack2<BF>(__uint_as_float(r[q4 * 8 + 2]) * inv, __uint_as_float(r[q4 * 8 + 3]) * inv);
+        w.z = pack2<BF>(__uint_as_float(r[q4 * 8 + 4]) * inv, __uint_as_float(r[q4 * 8 + 5]) * inv);
+        w.w = pack2<BF>(__uint_as_float(r[q4 * 8 + 6]) * inv, __uint_as_float(r[q4 * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(myrow + (((wg * 4 + q4) ^ (rit & 7)) << 4)) = w;
+      }
+      if (wg == 0 && row < S && p.lse) p.lse[(static_cast<long long>(seq) * p.heads + head) * S + row] = m + log2f(l);
+      tc_fence_before();
+      __syncthreads();
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 w;
-            w.x = pack2<BF>(__uint_as_float(r[q4 * 8 + 0]) * inv, __uint_as_float(r[q4 * 8 + 1]) * inv);
-            w.y = pack2<BF>(__uint_as_float(r[q4 * 8 + 2]) * inv, __uint_as_float(r[q4 * 8 + 3]) * inv);
-            w.z = pack2<BF>(__uint_as_float(r[q4 * 8 + 4]) * inv, __uint_as_float(r[q4 * 8 + 5]) * inv);
-            w.w = pack2<BF>(__uint_as_float(r[q4 * 8 + 6]) * inv, __uint_as_float(r[q4 * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = w;
-          }
+      for (int i = 0; i < 4; ++i) {
+        const int rr = r0 + 32 * i;
+        const int jj = qt * 128 + rr;
+        const uint4 v = *reinterpret_cast<const uint4*>(sP + rr * 128 + swz);
+        if (jj < S) {
+          uint16_t* dst = (jj == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
+                                               : p.o + rows(jj) * p.ld_o + head * DH;
+          *reinterpret_cast<uint4*>(dst + ch * 8) = v;
         }
       }
-      if (valid && p.lse) p.lse[(static_cast<long long>(seq) * p.heads + head) * p.S + row] = m + log2f(l);
+    }
+    ATTN_TRACE(tid == 0 && qt < 2, 10 + 10 * qt);
+    if (more) {
+      cp_async_wait_all();             // next query tile has landed
+      fence_proxy_async();
     }
     tc_fence_before();
-    __syncthreads();                   // every thread is done with TMEM / sQ before the next tile reuses them
+    __syncthreads();                   // every thread is done with TMEM / sP before the next tile reuses them
+    tc_fence_after();
+    ATTN_TRACE(tid == 0 && qt < 2, 11 + 10 * qt);
   }
   if (warp == 0) {
-    tc_fence_after();
+    __syncwarp();
     tmem_dealloc(tmem, 256);
   }
 }
@@ -1008,11 +1092,6 @@ __global__ void __launch_bounds__(128) sattn_fwd_tc_kernel(const SAttnParams p) 
 // MMAs of step s-1) while the softmax warps transform step s.
 // Shared memory: Q, dO [S16][64]; K, V [nkt*128][64] (zero rows beyond S); P^T ring 2 atoms; dS^T 4 atoms (one per query
 // chunk of the current key tile) -> ~215 KB at S=197, one CTA per SM; S <= 240.
-#define ATTN_TRACE(cond, slot)                                                                             \
-  do {                                                                                                   \
-    if (p.trace && (cond))                                                                               \
-      p.trace[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64() - t_start; \
-  } while (0)
 template <bool BF, bool DROP>
 __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams p) {
   const long long t_start = p.trace ? clock64() : 0;
@@ -1494,6 +1573,21 @@ extern "C" int alpro_debug_attn_trace(void* host_out, int64_t max_values) {
   return static_cast<int>(n / 64);
 }
 
+// ALPRO_ATTN_TRACE=1 (diagnostics only): zeroed per-CTA stamp buffer for the next tcgen05 attention launch, else null
+static long long* trace_buffer(size_t ctas, cudaStream_t st) {
+  const char* tr_env = getenv("ALPRO_ATTN_TRACE");
+  if (!(tr_env && tr_env[0] == '1')) return nullptr;
+  const size_t need = ctas * 64;
+  if (need > g_trace_len) {
+    if (g_trace) cudaFree(g_trace);
+    g_trace = nullptr;
+    g_trace_len = 0;
+    if (cudaMalloc(&g_trace, need * sizeof(long long)) == cudaSuccess) g_trace_len = need;
+  }
+  if (g_trace) cudaMemsetAsync(g_trace, 0, g_trace_len * sizeof(long long), st);
+  return g_trace;
+}
+
 static int fill_sattn(SAttnParams& p, const void* qkv, int64_t ld_qkv, const float* mask, int S, int nseq, int heads,
                       int fmt, int seq_div, int stride, int64_t clip_rows, float scale, float drop_p,
                       uint32_t drop_seed) {
@@ -1519,19 +1613,27 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
   const int S_pad = (S + 15) & ~15;
   dim3 grid(heads, nseq);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* tc_env = getenv("ALPRO_ATTN_TC");   // read per call so tests can switch implementations
-  if (tc_env && tc_env[0] == '1') {   // tcgen05 / TMEM forward (same outputs and lse format as the mma.sync kernel)
+  // tcgen05 / TMEM forward (same outputs and lse format as the mma.sync kernel; default for S >= 96: 0.143 vs 0.197 ms
+  // at 256x12 sequences of 197). ALPRO_ATTN_TC=0 forces mma.sync, =1 forces tcgen05; read per call so tests can switch.
+  const char* tc_env = getenv("ALPRO_ATTN_TC");
+  if (tc_env && (tc_env[0] == '0' || tc_env[0] == '1') ? tc_env[0] == '1' : S >= 96) {
     const size_t S32 = (S + 31) & ~31;
-    const size_t smem_tc = 1024 + 128 * 128 + S32 * 128 * 2 + 2 * 16384 + 256 * sizeof(float) + 64;
-    if (fmt == 1) {
-      rc = set_smem(sattn_fwd_tc_kernel<true>, smem_tc);
-      if (rc) return rc;
-      sattn_fwd_tc_kernel<true><<<grid, 128, smem_tc, st>>>(p);
-    } else {
-      rc = set_smem(sattn_fwd_tc_kernel<false>, smem_tc);
-      if (rc) return rc;
-      sattn_fwd_tc_kernel<false><<<grid, 128, smem_tc, st>>>(p);
-    }
+    const size_t smem_tc = 1024 + 128 * 128 + S32 * 128 * 2 + 2 * 16384 + (256 + 512) * sizeof(float) + 64;
+    p.trace = trace_buffer(static_cast<size_t>(heads) * nseq, st);
+#define LAUNCH_FWD_TC(BF, DR, MK)                                      \
+  do {                                                                 \
+    rc = set_smem(sattn_fwd_tc_kernel<BF, DR, MK>, smem_tc);           \
+    if (rc) return rc;                                                 \
+    sattn_fwd_tc_kernel<BF, DR, MK><<<grid, 256, smem_tc, st>>>(p);    \
+  } while (0)
+#define LAUNCH_FWD_TC_F(BF)                                                          \
+  do {                                                                               \
+    if (p.drop_thr) { if (mask) LAUNCH_FWD_TC(BF, true, true); else LAUNCH_FWD_TC(BF, true, false); }   \
+    else            { if (mask) LAUNCH_FWD_TC(BF, false, true); else LAUNCH_FWD_TC(BF, false, false); } \
+  } while (0)
+    if (fmt == 1) LAUNCH_FWD_TC_F(true); else LAUNCH_FWD_TC_F(false);
+#undef LAUNCH_FWD_TC_F
+#undef LAUNCH_FWD_TC
     ALPRO_CHECK_LAUNCH("alpro_seq_attn_fwd(tcgen05)");
     return 0;
   }
@@ -1587,20 +1689,7 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   const char* tc_env = getenv("ALPRO_ATTN_BWD_TC");
   const bool use_tc = S <= 240 && (tc_env && (tc_env[0] == '0' || tc_env[0] == '1') ? tc_env[0] == '1' : S >= 96);
   if (use_tc) {   // same inputs, outputs and dropout stream as the mma.sync kernel
-    const char* tr_env = getenv("ALPRO_ATTN_TRACE");
-    if (tr_env && tr_env[0] == '1') {   // diagnostics only: per-CTA phase stamps, read back by alpro_debug_attn_trace
-      const size_t need = static_cast<size_t>(heads) * nseq * 64;
-      if (need > g_trace_len) {
-        if (g_trace) cudaFree(g_trace);
-        g_trace = nullptr;
-        g_trace_len = 0;
-        if (cudaMalloc(&g_trace, need * sizeof(long long)) == cudaSuccess) g_trace_len = need;
-      }
-      if (g_trace) {
-        cudaMemsetAsync(g_trace, 0, g_trace_len * sizeof(long long), st);
-        p.trace = g_trace;
-      }
-    }
+    p.trace = trace_buffer(static_cast<size_t>(heads) * nseq, st);
     const size_t krows = static_cast<size_t>((S + 127) / 128) * 128;
     const size_t smem_tc = 1024 + 2 * static_cast<size_t>(S_pad) * 128 + 2 * krows * 128 + 6 * 16384 +
                            3 * 256 * sizeof(float) + 10 * sizeof(uint64_t) + 16;

@@ -129,7 +129,7 @@ def run_vit(N, T):
     return res
 
 
-def run_time(which):
+def run_time(which, order=(("mma", False, False), ("tc", True, True))):
     import torch
     from alpro_b200 import ops
     dev = "cuda"
@@ -181,8 +181,11 @@ def run_time(which):
                          drop, 5)
 
     outs = {}
-    for name, ftc, btc in (("mma", False, False), ("tc", True, True)):
+    for name, ftc, btc in order:
         setenv(ftc, btc)
+        if name == "tcf":   # forward only, last: leaves the forward kernel's stamps in the trace buffer
+            timeit(fwd, 2)
+            continue
         res[f"fwd_{name}_ms"] = round(timeit(fwd), 4)
         res[f"bwd_{name}_ms"] = round(timeit(bwd), 4)
         outs[name] = (o.float().clone(), dqkv.float().clone())
@@ -204,6 +207,31 @@ for _s in range(8):
     SLOTS[49 + 2 * _s] = f"  mma: s{_s} grads issued"
 SLOTS.update({36: "dkv0 wait", 37: "dkv0 acc_full", 38: "dkv0 stored", 39: "dkv1 wait", 40: "dkv1 acc_full",
               41: "dkv1 stored", 42: "dq stored", 43: "cta done"})
+
+
+FSLOTS = {1: "loads issued", 2: "tiles landed"}
+for _t in range(2):
+    FSLOTS.update({4 + 10 * _t: f"t{_t} S ready", 5 + 10 * _t: f"t{_t} max done", 6 + 10 * _t: f"t{_t} P half0 written",
+                   7 + 10 * _t: f"t{_t} PV half0 done", 8 + 10 * _t: f"t{_t} P half1 written",
+                   9 + 10 * _t: f"t{_t} PV half1 done", 10 + 10 * _t: f"t{_t} O stored", 11 + 10 * _t: f"t{_t} tile end"})
+
+
+def run_ftrace(which):
+    """Per-phase timeline of the tcgen05 forward kernel."""
+    import ctypes
+    import torch
+    os.environ["ALPRO_ATTN_TRACE"] = "1"
+    res = run_time(which, order=(("tc", True, True), ("mma", False, False), ("tcf", True, False)))
+    from alpro_b200 import _lib
+    n = 12 * 256 * 64
+    buf = (ctypes.c_int64 * n)()
+    nct = _lib.lib.alpro_debug_attn_trace(ctypes.cast(buf, ctypes.c_void_p), n)
+    t = torch.tensor(list(buf[: nct * 64]), dtype=torch.float64).view(nct, 64)
+    med = t.median(0).values
+    order = sorted((float(med[k]), k) for k in FSLOTS if float(med[k]) > 0)
+    res["timeline"] = [f"{int(v):6d} {FSLOTS[k]}" for v, k in order]
+    res["ctas"] = nct
+    return res
 
 
 def run_trace(which):
@@ -234,6 +262,8 @@ def run_case(case):
         return run_time(parts[1])
     if parts[0] == "trace":
         return run_trace(parts[1])
+    if parts[0] == "ftrace":
+        return run_ftrace(parts[1])
     raise SystemExit("unknown case " + case)
 
 
