@@ -263,10 +263,14 @@ def _attn_ref(q, k, v, scale, mask=None):
     return torch.softmax(s, -1) @ v
 
 
-@pytest.mark.parametrize("T", [2, 4, 8])
-def test_temporal_attention(T):
+@pytest.mark.parametrize("T,N,impl", [(2, 5, "cuda_core"), (4, 5, "cuda_core"), (8, 5, "cuda_core"), (8, 5, "tcgen05"),
+                                      (8, 16, "tcgen05"), (8, 196, "tcgen05")])
+def test_temporal_attention(T, N, impl, monkeypatch):
+    """T = 8 has two implementations (the library reads ALPRO_TATTN_TC on every call): CUDA-core registers/shuffles
+    and the tcgen05 block-diagonal kernels (16 units per 128-row tile; N = 5 and 196 end in partial tiles)."""
+    monkeypatch.setenv("ALPRO_TATTN_TC", "1" if impl == "tcgen05" else "0")
     ops = _ops()
-    B, N, heads = 2, 5, 3
+    B, heads = 2, 3
     d = heads * 64
     Sc = 1 + N * T
     gen = g(7)

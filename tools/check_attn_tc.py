@@ -252,6 +252,53 @@ def run_trace(which):
     return res
 
 
+def run_tattn(N, B, timed):
+    """Temporal attention: tcgen05 kernels (ALPRO_TATTN_TC=1) vs the CUDA-core kernels, T = 8."""
+    import torch
+    from alpro_b200 import ops
+    dev = "cuda"
+    T, heads = 8, (12 if timed else 3)
+    d = heads * 64
+    Sc = 1 + N * T
+    gen = torch.Generator(device=dev).manual_seed(11)
+    qkv = torch.randn(B * Sc, 3 * d, device=dev, generator=gen).half()
+    do = torch.randn(B * Sc, d, device=dev, generator=gen).half()
+    res = {}
+    outs = {}
+    flush = torch.empty(160 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    for name, flag in (("cc", "0"), ("tc", "1")):
+        os.environ["ALPRO_TATTN_TC"] = flag
+        o = torch.full((B * Sc, d), 7.0, device=dev, dtype=torch.float16)
+        dqkv = torch.full((B * Sc, 3 * d), 7.0, device=dev, dtype=torch.float16)
+        ops.temporal_attn_fwd(qkv, o, B, N, T, heads, 0.125)
+        ops.temporal_attn_bwd(qkv, do, dqkv, B, N, T, heads, 0.125)
+        torch.cuda.synchronize()
+        outs[name] = (o.float(), dqkv.float())
+        if timed:
+            for tag, fn in (("fwd", lambda: ops.temporal_attn_fwd(qkv, o, B, N, T, heads, 0.125)),
+                            ("bwd", lambda: ops.temporal_attn_bwd(qkv, do, dqkv, B, N, T, heads, 0.125))):
+                tot = 0.0
+                for _ in range(6):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    tot += e0.elapsed_time(e1)
+                res[f"{tag}_{name}_ms"] = round(tot / 6, 4)
+    res["fwd_tc_vs_cc"] = rel(outs["tc"][0], outs["cc"][0])
+    for k in ("dq", "dk", "dv"):
+        res[f"bwd_tc_vs_cc_{k}"] = rel(blocks(outs["tc"][1], d)[k], blocks(outs["cc"][1], d)[k])
+    res["finite"] = bool(torch.isfinite(outs["tc"][0]).all() and torch.isfinite(outs["tc"][1]).all())
+    res["cls_zero"] = float(outs["tc"][0].view(B, Sc, d)[:, 0].abs().max() + outs["tc"][1].view(B, Sc, 3 * d)[:, 0].abs().max())
+    if timed:
+        rows = B * Sc
+        res["fwd_tc_GBs"] = round(rows * d * 2 * 4 / (res["fwd_tc_ms"] * 1e-3) / 1e9, 1)
+        res["bwd_tc_GBs"] = round(rows * d * 2 * 7 / (res["bwd_tc_ms"] * 1e-3) / 1e9, 1)
+    return res
+
+
 def run_case(case):
     parts = case.split(":")
     if parts[0] == "bert":
@@ -262,6 +309,8 @@ def run_case(case):
         return run_time(parts[1])
     if parts[0] == "trace":
         return run_trace(parts[1])
+    if parts[0] == "tattn":
+        return run_tattn(int(parts[1]), int(parts[2]), len(parts) > 3)
     if parts[0] == "ftrace":
         return run_ftrace(parts[1])
     raise SystemExit("unknown case " + case)
