@@ -293,6 +293,11 @@ layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long l
   auto sx = [&](int s) { return wbase + (s * 3 + 0) * ARR; };
   auto sdy = [&](int s) { return wbase + (s * 3 + 1) * ARR; };
   auto sdx = [&](int s) { return wbase + (s * 3 + 2) * ARR; };
+  // gamma is the same for every row: one copy in shared memory behind the staging buffers (it was re-read through
+  // __ldg twice per row and element: long-scoreboard stalls on L1/L2 hits, ncu r01p)
+  float4* sgam = reinterpret_cast<float4*>(lnb_smem) + static_cast<size_t>(LNB_WARPS) * (2 * 3 * ARR);
+  for (int c = threadIdx.x; c < nv; c += blockDim.x) sgam[c] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+  __syncthreads();
   auto issue = [&](long long row, int s) {
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
@@ -313,9 +318,24 @@ layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long l
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdx(s) + c)),
                        "l"(reinterpret_cast<const float4*>(dx32 + row * lddx) + c)
                        : "memory");
+        // the 16-bit multiplier rows are read straight from global when their row is processed: pull them into L2 now
+        if (dx16_mul16)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint2*>(dx16_mul16 + row * lddxmul) + c));
+        if (dy_mul16)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint2*>(dy_mul16 + row * lddymul) + c));
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // per-row scalars of the NEXT row are fetched one iteration ahead (a dependent global load per row otherwise)
+  struct RowScalars { float mu, rs, cs, rsv; };
+  auto row_scalars = [&](long long row) {
+    RowScalars r;
+    r.mu = mean[row];
+    r.rs = rstd[row];
+    r.rsv = dx16_row_scale ? dx16_row_scale[row] : 1.f;
+    r.cs = colsum_row_scale ? colsum_row_scale[row] : r.rsv;
+    return r;
   };
 
   float4 ag[NV4], ab[NV4], ac[NV4];
@@ -324,17 +344,22 @@ layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long l
 
   const long long stride = static_cast<long long>(gridDim.x) * LNB_WARPS;
   long long row = static_cast<long long>(blockIdx.x) * LNB_WARPS + warp;
-  if (row < M) issue(row, 0);
+  RowScalars cur{0.f, 0.f, 1.f, 1.f}, nxt{0.f, 0.f, 1.f, 1.f};
+  if (row < M) {
+    issue(row, 0);
+    cur = row_scalars(row);
+  }
   int s = 0;
-  for (; row < M; row += stride, s ^= 1) {
+  for (; row < M; row += stride, s ^= 1, cur = nxt) {
     const long long nrow = row + stride;
     if (nrow < M) {
       issue(nrow, s ^ 1);
+      nxt = row_scalars(nrow);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    const float mu = mean[row], rs = rstd[row];
+    const float mu = cur.mu, rs = cur.rs;
     float4 xv[NV4], dv[NV4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -356,7 +381,7 @@ layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long l
           dv[i].x *= f16_to_32(static_cast<uint16_t>(mw.x & 0xffff), fmt); dv[i].y *= f16_to_32(static_cast<uint16_t>(mw.x >> 16), fmt);
           dv[i].z *= f16_to_32(static_cast<uint16_t>(mw.y & 0xffff), fmt); dv[i].w *= f16_to_32(static_cast<uint16_t>(mw.y >> 16), fmt);
         }
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 gm = sgam[c];
         const float hx = (xv[i].x - mu) * rs, hy = (xv[i].y - mu) * rs, hz = (xv[i].z - mu) * rs, hw = (xv[i].w - mu) * rs;
         const float gx = dv[i].x * gm.x, gy = dv[i].y * gm.y, gz = dv[i].z * gm.z, gw = dv[i].w * gm.w;
         s1 += (gx + gy) + (gz + gw);
@@ -368,14 +393,13 @@ layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long l
     const float c1 = warp_sum(s1) / d, c2 = warp_sum(s2) / d;
     const bool zero16 = zero_period > 0 && (row % zero_period) == 0;
     const bool cs_on = colsum != nullptr && !(colsum_zero_period > 0 && (row % colsum_zero_period) == 0);
-    const float cs = colsum_row_scale ? colsum_row_scale[row] : (dx16_row_scale ? dx16_row_scale[row] : 1.f);
-    const float rsv = dx16_row_scale ? dx16_row_scale[row] : 1.f;
+    const float cs = cur.cs, rsv = cur.rsv;
     float4* dxrow = reinterpret_cast<float4*>(dx32 + row * lddx);
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 gm = sgam[c];
         float4 o;
         o.x = rs * (dv[i].x * gm.x - c1 - (xv[i].x - mu) * rs * c2);
         o.y = rs * (dv[i].y * gm.y - c1 - (xv[i].y - mu) * rs * c2);
@@ -830,7 +854,8 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
                            (lddx % 4) == 0 && aligned16(dy) && (lddy % 4) == 0;
     if (use_async) {
       const int nv4 = d <= 256 ? 2 : 6;
-      const size_t smem_a = static_cast<size_t>(LNB_WARPS) * 2 * 3 * nv4 * 32 * sizeof(float4);
+      const size_t smem_a = static_cast<size_t>(LNB_WARPS) * 2 * 3 * nv4 * 32 * sizeof(float4) +
+                            static_cast<size_t>(nv4) * 32 * sizeof(float4);   // staging + one copy of gamma
       int grid_a = static_cast<int>(cdiv(M, LNB_WARPS));
       if (grid_a > num_sms()) grid_a = num_sms();
 #define ALPRO_LN_BWD_A(NV)                                                                                             \

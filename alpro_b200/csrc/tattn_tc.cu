@@ -93,13 +93,15 @@ __device__ __forceinline__ void decode_item(const Params& p, int item, int& b, i
 
 // ------------------------------------------------------------------------------------------------ forward
 namespace fwd {
-constexpr int NST = 2;                                  // operand stages (Q, K, V tiles = 48 KB each)
+constexpr int NST = 3;                                  // operand stages (Q, K, V tiles = 48 KB each): two items of
+                                                        // loads in flight while a third is consumed
 constexpr int STAGE_BYTES = 3 * TILE;
 constexpr int P_BYTES = 2 * TILE;                       // block-diagonal [128][128] 16-bit = two 64-key atoms
 constexpr int OFF_P = NST * STAGE_BYTES;                // 2 P buffers
-constexpr int OFF_O = OFF_P + 2 * P_BYTES;              // 2 O staging tiles (TMA store source)
-constexpr int OFF_BAR = OFF_O + 2 * TILE;
+constexpr int OFF_O = OFF_P + 2 * P_BYTES;              // 1 O staging tile (TMA store source)
+constexpr int OFF_BAR = OFF_O + TILE;
 constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int THREADS = 192;
 
 template <bool BF>
@@ -261,9 +263,9 @@ tattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[a]);
-      if (etid == 0) bulk_wait_read<1>();   // the store of item k-2 has drained staging tile a
+      if (etid == 0) bulk_wait_read<0>();   // the store of the previous item has drained the staging tile
       named_bar_sync(1, 128);
-      uint8_t* orow = sO + a * TILE + r * 128;
+      uint8_t* orow = sO + r * 128;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         uint4 x, y;
@@ -281,7 +283,7 @@ tattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       fence_proxy_async();
       named_bar_sync(1, 128);
       if (etid == 0) {
-        tma_store_3d(&tmO, sO + a * TILE, h * DH, 1 + g * ROWS, b);
+        tma_store_3d(&tmO, sO, h * DH, 1 + g * ROWS, b);
         bulk_commit();
       }
     };
@@ -313,6 +315,7 @@ constexpr int OFF_P = NST * STAGE_BYTES;                // P  (block-diagonal [1
 constexpr int OFF_DS = OFF_P + P_BYTES;                 // dS (same layout)
 constexpr int OFF_BAR = OFF_DS + P_BYTES;
 constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int THREADS = 192;
 // TMEM columns (single-buffered): S, dP (128 each), dQ, dK, dV (64 each)
 constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 320, COL_DV = 384;

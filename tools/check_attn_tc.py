@@ -299,6 +299,48 @@ def run_tattn(N, B, timed):
     return res
 
 
+def run_lnbwd(which):
+    """Timing of layernorm_bwd at the two large shapes of the step (video token stream / fusion stream with dropout)."""
+    import torch
+    from alpro_b200 import ops
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(5)
+    d = 768
+    M = 50208 if which == "video" else 30336
+    x = torch.randn(M, d, device=dev, generator=gen)
+    mean, rstd = x.mean(1).contiguous(), (1.0 / x.std(1)).contiguous()
+    gamma = torch.randn(d, device=dev, generator=gen)
+    dx = torch.randn(M, d, device=dev, generator=gen)
+    dx16 = torch.empty(M, d, device=dev, dtype=torch.float16)
+    dg, db, cs = (torch.zeros(d, device=dev) for _ in range(3))
+    if which == "video":
+        dy = torch.randn(M, d, device=dev, generator=gen).half()
+        rsc = torch.rand(M, device=dev, generator=gen)
+        fn = lambda: ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, 1, dx16=dx16, dgamma=dg, dbeta=db, param_scale=1.0,
+                                       colsum=cs, dx16_row_scale=rsc)
+        nbytes = M * d * (2 + 4 + 4 + 4 + 2)
+    else:
+        dy = torch.randn(M, d, device=dev, generator=gen)
+        mask = (torch.rand(M, d, device=dev, generator=gen) > 0.1).half()
+        fn = lambda: ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, 0, dx16=dx16, dgamma=dg, dbeta=db, param_scale=1.0,
+                                       colsum=cs, dx16_mul16=mask)
+        nbytes = M * d * (4 + 4 + 4 + 2 + 2)
+    flush = torch.empty(160 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    for _ in range(3):
+        fn()
+    tot = 0.0
+    for _ in range(6):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / 6
+    return {"M": M, "ms": round(ms, 4), "GBs": round(nbytes / (ms * 1e-3) / 1e9, 1)}
+
+
 def run_case(case):
     parts = case.split(":")
     if parts[0] == "bert":
@@ -309,6 +351,8 @@ def run_case(case):
         return run_time(parts[1])
     if parts[0] == "trace":
         return run_trace(parts[1])
+    if parts[0] == "lnbwd":
+        return run_lnbwd(parts[1])
     if parts[0] == "tattn":
         return run_tattn(int(parts[1]), int(parts[2]), len(parts) > 3)
     if parts[0] == "ftrace":
