@@ -338,6 +338,7 @@ struct SAttnParams {
   uint32_t drop_thr, drop_seed;
   float drop_scale;
   long long* trace;      // diagnostics (ALPRO_ATTN_TRACE=1): 64 clock64() stamps per CTA, null in normal runs
+  int stagger;           // tcgen05 backward: first-wave CTA i starts (i % 4) * stagger cycles late (0 = off)
 };
 
 // mask/keep factors of the key pair (2*jp, 2*jp+1) for query row i of (seq, head): one counter-hash per pair
@@ -1126,6 +1127,17 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role branches stay uniform
   constexpr int fmt = BF ? 1 : 0;
+  // One CTA per SM and every unit costs the same, so all SMs load, compute and store in lockstep: HBM idles while
+  // they compute and is oversubscribed while they load. ALPRO_ATTN_STAGGER=<cycles> starts the first wave in four
+  // phases so that the SMs stay out of step for the whole launch (experiment; off by default).
+  if (p.stagger > 0) {
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin < 148) {
+      const long long until = clock64() + static_cast<long long>(lin & 3) * p.stagger;
+      while (clock64() < until) {
+      }
+    }
+  }
 
   if (warp == 8) {
     if (lane == 0) {
@@ -1714,6 +1726,10 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   const bool use_tc = S <= 240 && (tc_env && (tc_env[0] == '0' || tc_env[0] == '1') ? tc_env[0] == '1' : S >= 96);
   if (use_tc) {   // same inputs, outputs and dropout stream as the mma.sync kernel
     p.trace = trace_buffer(static_cast<size_t>(heads) * nseq, st);
+    {
+      const char* sg = getenv("ALPRO_ATTN_STAGGER");
+      p.stagger = sg ? atoi(sg) : 0;
+    }
     const size_t krows = static_cast<size_t>((S + 127) / 128) * 128;
     const size_t smem_tc = 1024 + 2 * static_cast<size_t>(S_pad) * 128 + 2 * krows * 128 + 6 * 16384 +
                            3 * 256 * sizeof(float) + 10 * sizeof(uint64_t) + 16;

@@ -351,6 +351,10 @@ def run_case(case):
         return run_time(parts[1])
     if parts[0] == "trace":
         return run_trace(parts[1])
+    if parts[0] == "stagger":   # stagger:<cycles>: time:vit with ALPRO_ATTN_STAGGER set
+        os.environ["ALPRO_ATTN_STAGGER"] = parts[1]
+        r = run_time("vit")
+        return {k: v for k, v in r.items() if k in ("bwd_tc_ms", "bwd_tc_vs_mma")}
     if parts[0] == "lnbwd":
         return run_lnbwd(parts[1])
     if parts[0] == "tattn":
