@@ -147,7 +147,9 @@ int alpro_dropout_mask(void* out16, int fmt, int64_t n, float p, uint32_t seed, 
  * Attention (alpro_b200/csrc/attention.cu), head_dim = 64
  */
 /* temporal attention over the T frames of each patch position (vit.py:81-100 via :146-157); T in {1,2,4,8}.
- * qkv [B*(1+N*T), 3d] canonical rows; cls rows are skipped (zero-filled in the outputs). */
+ * qkv [B*(1+N*T), 3d] canonical rows; cls rows are skipped (zero-filled in the outputs).
+ * T = 8 with 16-byte-aligned rows runs the TMA + tcgen05 kernels of tattn_tc.cu (16 units per 128-row tile);
+ * ALPRO_TATTN_TC=0 in the environment selects the CUDA-core kernels (read on every call). */
 int alpro_temporal_attn_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int B, int N, int T, int heads,
                             int fmt, float scale, void* stream);
 int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const void* dout, int64_t ld_dout, void* dqkv,
@@ -156,7 +158,10 @@ int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const void* dout, i
  * xbert.py:263-346). Token j of sequence s lives at row (s/seq_div)*clip_rows + (j==0 ? 0 : 1 + s%seq_div + (j-1)*stride):
  *   BERT: seq_div=1, stride=1, clip_rows=S.   TimeSformer spatial: seq_div=T, stride=T, clip_rows=1+N*T, S=1+N.
  * With seq_div>1 the per-frame cls outputs go to cls_o [nseq,d] (mean taken by alpro_cls_mean_fwd). lse: [nseq,heads,S]. */
-/* drop_p > 0: train-mode dropout of the attention probabilities (xbert.py:331) from the stateless hash (drop_seed). */
+/* drop_p > 0: train-mode dropout of the attention probabilities (xbert.py:331) from the stateless hash (drop_seed).
+ * Implementations (same outputs, lse format and dropout stream; the environment is read on every call):
+ *   forward : tcgen05/TMEM kernel for S >= 96, mma.sync kernel below; ALPRO_ATTN_TC=0 / 1 forces mma.sync / tcgen05
+ *   backward: tcgen05/TMEM kernel for 96 <= S <= 240, mma.sync otherwise; ALPRO_ATTN_BWD_TC=0 / 1 forces one of them */
 int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* mask, void* o, int64_t ld_o, void* cls_o, float* lse,
                        int S, int nseq, int heads, int fmt, int seq_div, int stride, int64_t clip_rows, float scale,
                        float drop_p, uint32_t drop_seed, void* stream);
