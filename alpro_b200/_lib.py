@@ -27,6 +27,7 @@ class GemmEpilogue(ctypes.Structure):
         ("act", ctypes.c_int32), ("skip_period", ctypes.c_int32), ("split_k", ctypes.c_int32),
         ("alpha", c_float),
         ("row_scale_acc", c_void_p), ("row_scale_bias", c_void_p),
+        ("bias2", c_void_p),
     ]
 
 

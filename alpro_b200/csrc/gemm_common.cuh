@@ -26,6 +26,7 @@ struct GemmKParams {
   int skip_period;
   const float* rs_acc;   // optional per-row scale of (alpha*acc)   [M]  (drop_path: mask/keep of the row's sample)
   const float* rs_bias;  // optional per-row scale of the bias term  [M]  (defaults to rs_acc)
+  const float* bias2;    // optional second, never row-scaled bias [N] (residual modes; skip rows keep the residual)
   int vec_ok;  // all leading dims / pointers allow vector accesses on 4-column groups
   float alpha;
 };
@@ -173,11 +174,13 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, float (&v)[N
       for (int j = 0; j < 4; ++j) v[i][j] = u[i][j] > 0.f ? v[i][j] : 0.f;
   }
   if (has_resid) {
+    float c2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias2) load4_32(p.bias2 + col, c2, full, ncol);
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       const bool skip = p.skip_period > 0 && (row[i] % p.skip_period) == 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = skip ? rr[i][j] : v[i][j] + rr[i][j];
+      for (int j = 0; j < 4; ++j) v[i][j] = skip ? rr[i][j] : v[i][j] + rr[i][j] + c2[j];
     }
   }
 #pragma unroll

@@ -445,8 +445,12 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
   p.alpha = ep->alpha;
   p.rs_acc = ep->row_scale_acc;
   p.rs_bias = ep->row_scale_bias;
+  p.bias2 = ep->bias2;
+  ALPRO_REQUIRE(!p.bias2 || (p.resid && p.out32 && p.act == ALPRO_ACT_NONE),
+                "alpro_gemm16: bias2 is an option of the residual epilogue (resid + out32, no activation)");
   bool vec = true;
   if (p.bias) vec = vec && aligned16(p.bias);
+  if (p.bias2) vec = vec && aligned16(p.bias2);
   if (p.out32) vec = vec && aligned16(p.out32) && (p.ld32 % 4) == 0;
   if (p.resid) vec = vec && aligned16(p.resid) && (p.ldresid % 4) == 0;
   if (p.out16) vec = vec && aligned16(p.out16) && (p.ld16 % 4) == 0;
@@ -476,7 +480,8 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
     const int clusters = work < num_sms() / 2 ? work : num_sms() / 2;
     // TMA-store epilogue (gemm_tc3.cu): outputs (and the residual / saved-derivative input) whose rows the TMA unit can
     // address (16-byte aligned base and pitch), whole 32-column chunks, one 16-bit storage format.
-    bool tma_epi = use_tma_epilogue() && (N % 32) == 0 && (!p.bias || aligned16(p.bias));
+    bool tma_epi = use_tma_epilogue() && (N % 32) == 0 && (!p.bias || aligned16(p.bias)) &&
+                   (!p.bias2 || aligned16(p.bias2));
     if (mode == E_OUT16 || mode == E_GELU_SAVE || mode == E_GELU_GRAD) {
       tma_epi = tma_epi && aligned16(p.out16) && (p.ld16 % 8) == 0;
       if (mode == E_GELU_SAVE && p.out16b)

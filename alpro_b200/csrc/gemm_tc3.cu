@@ -69,6 +69,7 @@ __device__ __forceinline__ uint32_t stage_off(int row, int c) { return row * 64 
 // Per-row epilogue scalars of this lane's row: v = ra * acc + rb * bias (ra already includes alpha).
 struct RowScale {
   float ra, rb;
+  float rc;   // factor of the second (never row-scaled) bias: 1, or 0 on rows that keep the plain residual
 };
 
 // One 32-column chunk of one accumulator row (this lane's): r[] raw fp32 accumulators -> packed 16-bit results in pk[]
@@ -123,6 +124,10 @@ __device__ __forceinline__ void chunk_resid(const GemmKParams& p, const uint32_t
     x.y = fmaf(__uint_as_float(r[4 * g + 1]), rs.ra, fmaf(b.y, rs.rb, x.y));
     x.z = fmaf(__uint_as_float(r[4 * g + 2]), rs.ra, fmaf(b.z, rs.rb, x.z));
     x.w = fmaf(__uint_as_float(r[4 * g + 3]), rs.ra, fmaf(b.w, rs.rb, x.w));
+    if (p.bias2) {   // warp-uniform
+      const float4 c = __ldg(reinterpret_cast<const float4*>(p.bias2 + col0 + 4 * g));
+      x.x = fmaf(c.x, rs.rc, x.x); x.y = fmaf(c.y, rs.rc, x.y); x.z = fmaf(c.z, rs.rc, x.z); x.w = fmaf(c.w, rs.rc, x.w);
+    }
     *reinterpret_cast<float4*>(buf + stage_off(lane, g)) = x;
   }
 }
@@ -304,6 +309,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       RowScale rs;
       rs.ra = p.alpha;
       rs.rb = 1.f;
+      rs.rc = 1.f;
       if (MODE != E_GELU_GRAD && MODE != E_ATOMIC) {
         const int row = min(row0 + lane, p.M - 1);
         if (p.rs_acc) {
@@ -311,7 +317,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           rs.rb = p.rs_bias ? __ldg(p.rs_bias + row) : ra;
           rs.ra *= ra;
         }
-        if (MODE == E_RESID_OUT32 && p.skip_period > 0 && (row % p.skip_period) == 0) rs.ra = rs.rb = 0.f;
+        if (MODE == E_RESID_OUT32 && p.skip_period > 0 && (row % p.skip_period) == 0) rs.ra = rs.rb = rs.rc = 0.f;
       }
       const bool row_scaled = p.rs_acc != nullptr;   // warp-uniform
       const int nvalid = min(NCH, max(0, (p.N - chunk_col(w, 0) + CW - 1) / CW));   // warp-uniform

@@ -10,6 +10,7 @@ Layout / precision choices:
     default) with fp32 TMEM accumulation; the backward pass carries gradients multiplied by a static loss scale S.
 """
 import math
+import os
 
 import torch
 
@@ -46,6 +47,27 @@ class OperandCache:
             dst = ent[1] if ent is not None else _empty(shape2d or tuple(src.shape), self.dtype, src.device)
             ops.cast16(src.contiguous().view(-1), dst.view(-1))
             ent = (key, dst)
+            self._c[name] = ent
+        return ent[1]
+
+    def get_fused_linear(self, name, w2, w1, b1):
+        """Operand of the composition x -> W2 (W1 x + b1): (W2 W1 as a 16-bit [out, in] operand, W2 b1 as fp32).
+        TimeSformer applies temporal_fc directly to the (DropPath-scaled) output of temporal_attn.proj (vit.py:157-161),
+        so one GEMM with the composed weight stands for the two Linear maps. Refreshed when a parameter changes."""
+        ent = self._c.get(name)
+        key = self._key((w2, w1, b1))
+        if ent is None or ent[0] != key:
+            w2_16 = self.get(name + "#w2", w2)
+            w1_16 = self.get(name + "#w1", w1)
+            n_out, n_in = w2.shape[0], w1.shape[1]
+            wc = ent[1][0] if ent is not None else _empty((n_out, n_in), self.dtype, w2.device)
+            c1 = ent[1][1] if ent is not None else _empty((n_out,), torch.float32, w2.device)
+            # Wc[i, j] = sum_k W2[i, k] W1[k, j]: A = W2 (K-major), B = W1 stored [k][j] = MN-major
+            ops.gemm16(w2_16, w1_16, b_layout=MNMAJOR, out16=wc)
+            # c1[i] = sum_k b1[k] W2[i, k]  (fp32)
+            ops.small_linear_fwd(b1.detach().view(1, -1), b1.numel(), w2.detach(), None, c1.view(1, -1), 1, n_out,
+                                 w2.shape[1])
+            ent = (key, (wc, c1))
             self._c[name] = ent
         return ent[1]
 
@@ -244,6 +266,11 @@ class VisualEncoder:
                 t = scratch[name] = _empty(shape, dtype, dev)
             return t
 
+        # temporal_attn.proj and temporal_fc run as one composed Linear (one 385 MB HBM-bound GEMM less per block in the
+        # forward, one dgrad + one wgrad less in the backward); ALPRO_FUSE_TFC=0 keeps the two Linear maps (read per call)
+        fuse_tfc = os.environ.get("ALPRO_FUSE_TFC", "1") != "0"
+        if save:
+            ctx["fuse_tfc"] = fuse_tfc
         for i in range(self.depth):
             b = f"{p}blocks.{i}."
             g = lambda n: P[b + n].detach()
@@ -258,11 +285,19 @@ class VisualEncoder:
             ops.gemm16(a_t, w("temporal_attn.qkv.weight"), bias=g("temporal_attn.qkv.bias"), out16=qkv_t)
             o_t = buf("o_t", (M, d), dt)
             ops.temporal_attn_fwd(qkv_t, o_t, B, N, T, heads, scale)
-            p_t = buf("p_t", (M, d), dt)
-            ops.gemm16(o_t, w("temporal_attn.proj.weight"), bias=g("temporal_attn.proj.bias"), out16=p_t,
-                       row_scale=dp["rs_t"] if dp else None)
             x1 = buf("x1", (M, d), torch.float32)
-            ops.gemm16(p_t, w("temporal_fc.weight"), bias=g("temporal_fc.bias"), resid=x, skip_period=Sc, out32=x1)
+            if fuse_tfc:
+                # proj -> DropPath -> temporal_fc as ONE GEMM: x1 = x + s (o Wc^T + W_fc b_proj) + b_fc, Wc = W_fc W_proj
+                p_t = None
+                wc, c1 = W.get_fused_linear(b + "temporal_fc*proj", P[b + "temporal_fc.weight"],
+                                            P[b + "temporal_attn.proj.weight"], P[b + "temporal_attn.proj.bias"])
+                ops.gemm16(o_t, wc, bias=c1, bias2=g("temporal_fc.bias"), resid=x, skip_period=Sc, out32=x1,
+                           row_scale=dp["rs_t"] if dp else None)
+            else:
+                p_t = buf("p_t", (M, d), dt)
+                ops.gemm16(o_t, w("temporal_attn.proj.weight"), bias=g("temporal_attn.proj.bias"), out16=p_t,
+                           row_scale=dp["rs_t"] if dp else None)
+                ops.gemm16(p_t, w("temporal_fc.weight"), bias=g("temporal_fc.bias"), resid=x, skip_period=Sc, out32=x1)
             # ---- spatial attention branch (vit.py:165-196)
             a_s = buf("a_s", (M, d), dt)
             st_s = buf("st_s", (2, M), torch.float32)
@@ -330,6 +365,12 @@ class VisualEncoder:
         da = _empty((M, d), dt, dev)
         db_ = _empty((M, d), dt, dev)
         scratch = _empty((B * T, 3 * d), torch.float32, dev)
+        ones_rows = None
+        if ctx.get("fuse_tfc"):
+            dwc32 = _empty((d, d), torch.float32, dev)
+            dwc16 = _empty((d, d), dt, dev)
+            v32 = torch.zeros(d, device=dev)
+            ws = 256.0
 
         def wgrad(dy16, x16, wname, bname=None, zero_period=0):
             # bname=None: the bias gradient was already produced by the LayerNorm backward that emitted dy16
@@ -362,15 +403,44 @@ class VisualEncoder:
             ops.gemm16(d3, w("attn.qkv.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d3, c["a_s"], b + "attn.qkv.weight", b + "attn.qkv.bias")
             # dx16 <- grad wrt x1 with cls rows zeroed (the temporal branch never touches cls rows)
-            ops.layernorm_bwd(da, c["x1"], c["st_s"][0], c["st_s"][1], g("norm1.weight"), dx, 1, dx16=dx16,
-                              zero_period=Sc, dgamma=G[b + "norm1.weight"], dbeta=G[b + "norm1.bias"],
-                              param_scale=inv, colsum=G[b + "temporal_fc.bias"], colsum_zero_period=Sc)
-            # ---- temporal attention
-            ops.gemm16(dx16, w("temporal_fc.weight"), b_layout=MNMAJOR, out16=da,        # d p_t
-                       row_scale=dp["rs_t"] if dp else None)
-            wgrad(dx16, c["p_t"], b + "temporal_fc.weight")
-            ops.gemm16(da, w("temporal_attn.proj.weight"), b_layout=MNMAJOR, out16=db_)  # d o_t
-            wgrad(da, c["o_t"], b + "temporal_attn.proj.weight", b + "temporal_attn.proj.bias")
+            if ctx.get("fuse_tfc"):
+                # composed Linear (see forward): dx16 carries the DropPath factor s of the branch, the column sums stay
+                # unscaled (they are the gradient of temporal_fc.bias, which sits behind the DropPath)
+                if dp and ones_rows is None:
+                    ones_rows = torch.ones(M, device=dev)
+                ops.layernorm_bwd(da, c["x1"], c["st_s"][0], c["st_s"][1], g("norm1.weight"), dx, 1, dx16=dx16,
+                                  zero_period=Sc, dgamma=G[b + "norm1.weight"], dbeta=G[b + "norm1.bias"],
+                                  param_scale=inv, colsum=G[b + "temporal_fc.bias"], colsum_zero_period=Sc,
+                                  dx16_row_scale=dp["rs_t"] if dp else None, colsum_row_scale=ones_rows if dp else None)
+                wc, _ = W.get_fused_linear(b + "temporal_fc*proj", P[b + "temporal_fc.weight"],
+                                           P[b + "temporal_attn.proj.weight"], P[b + "temporal_attn.proj.bias"])
+                ops.gemm16(dx16, wc, b_layout=MNMAJOR, out16=db_)                             # d o_t
+                # dWc = (s * d_res)^T o_t, kept at ws x its true scale so that its 16-bit copy neither overflows (a weight
+                # gradient sums over all tokens: the loss scale S of the activation gradients would be too much) nor
+                # underflows; v = colsum(s * d_res) stays fp32 at the loss scale
+                dwc32.zero_()
+                ops.gemm16(dx16, c["o_t"], a_layout=MNMAJOR, b_layout=MNMAJOR, out32=dwc32, split_k=-1, alpha=ws * inv)
+                ops.colsum(dx16, v32, 1.0, 0)
+                ops.cast16(dwc32.view(-1), dwc16.view(-1))
+                wfc16, wp16 = w("temporal_fc.weight"), w("temporal_attn.proj.weight")
+                # dW_fc += dWc W_proj^T + v (x) b_proj ;  dW_proj += W_fc^T dWc ;  db_proj += W_fc^T v
+                ops.gemm16(dwc16, wp16, out32=G[b + "temporal_fc.weight"], split_k=2, alpha=1.0 / ws)
+                ops.gemm16(wfc16, dwc16, a_layout=MNMAJOR, b_layout=MNMAJOR, out32=G[b + "temporal_attn.proj.weight"],
+                           split_k=2, alpha=1.0 / ws)
+                ops.small_linear_bwd(v32.view(1, -1), d, None, g("temporal_attn.proj.bias").view(1, -1), d,
+                                     P[b + "temporal_fc.weight"].detach(), G[b + "temporal_attn.proj.bias"].view(1, -1),
+                                     d, True, G[b + "temporal_fc.weight"], None, True, 1, d, d, alpha=inv)
+                v32.zero_()
+            else:
+                ops.layernorm_bwd(da, c["x1"], c["st_s"][0], c["st_s"][1], g("norm1.weight"), dx, 1, dx16=dx16,
+                                  zero_period=Sc, dgamma=G[b + "norm1.weight"], dbeta=G[b + "norm1.bias"],
+                                  param_scale=inv, colsum=G[b + "temporal_fc.bias"], colsum_zero_period=Sc)
+                # ---- temporal attention
+                ops.gemm16(dx16, w("temporal_fc.weight"), b_layout=MNMAJOR, out16=da,        # d p_t
+                           row_scale=dp["rs_t"] if dp else None)
+                wgrad(dx16, c["p_t"], b + "temporal_fc.weight")
+                ops.gemm16(da, w("temporal_attn.proj.weight"), b_layout=MNMAJOR, out16=db_)  # d o_t
+                wgrad(da, c["o_t"], b + "temporal_attn.proj.weight", b + "temporal_attn.proj.bias")
             ops.temporal_attn_bwd(c["qkv_t"], db_, d3, B, N, T, heads, scale)
             ops.gemm16(d3, w("temporal_attn.qkv.weight"), b_layout=MNMAJOR, out16=da)
             wgrad(d3, c["a_t"], b + "temporal_attn.qkv.weight", b + "temporal_attn.qkv.bias")
@@ -951,3 +1021,6 @@ class _PrefixedCache:
 
     def get_cat(self, name, ps):
         return self.cache.get_cat(self.prefix + name, ps)
+
+    def get_fused_linear(self, name, w2, w1, b1):
+        return self.cache.get_fused_linear(self.prefix + name, w2, w1, b1)

@@ -43,7 +43,8 @@ def _row_major_2d(t, name):
 
 
 def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, aux=None, resid=None, out32=None,
-           out16=None, out16b=None, skip_period=0, split_k=0, alpha=1.0, row_scale=None, row_scale_bias=None):
+           out16=None, out16b=None, skip_period=0, split_k=0, alpha=1.0, row_scale=None, row_scale_bias=None,
+           bias2=None):
     """acc[m,n] = sum_k A(m,k) B(n,k) on tcgen05 tensor cores, fused epilogue (see include/alpro_b200.h).
 
     a: [M,K] (K-major) or [K,M] (MN-major) 16-bit; b: [N,K] (K-major) or [K,N] (MN-major) 16-bit.
@@ -94,6 +95,9 @@ def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, a
     ep.alpha = alpha
     ep.row_scale_acc = _ptr(row_scale)
     ep.row_scale_bias = _ptr(row_scale_bias)
+    ep.bias2 = _ptr(bias2)
+    if bias2 is not None:
+        assert bias2.dtype == torch.float32 and bias2.numel() == N and bias2.is_contiguous()
     prof = GEMM_PROFILE
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)

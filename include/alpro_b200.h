@@ -77,6 +77,10 @@ typedef struct AlproGemmEpilogue {
   const float* row_scale_acc;  /* optional [M]: v = row_scale_acc[m]*alpha*acc + row_scale_bias[m]*bias   (DropPath: the
                                   per-sample mask/keep_prob of vit_utils.py:137-162 expanded to token rows) */
   const float* row_scale_bias; /* optional [M]; defaults to row_scale_acc */
+  const float* bias2;          /* optional [N], residual modes only: a second bias that is NOT row-scaled,
+                                  out = resid + row_scale_acc*alpha*acc + row_scale_bias*bias + bias2 (skip_period rows
+                                  keep the plain residual). Lets one GEMM stand for Linear -> DropPath -> Linear:
+                                  temporal_attn.proj -> drop_path -> temporal_fc, vit.py:157-161 */
 } AlproGemmEpilogue;
 
 int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,

@@ -42,6 +42,9 @@ GEMM_CASES = [
     (256, 512, 1000, 1, 0, torch.float16, {"out32": 1}),
     (320, 1001, 192, 0, 0, torch.float16, {"bias": 1, "out32": 1}),          # unaligned N (vocab-style)
     (640, 192, 768, 0, 0, torch.float16, {"bias": 1, "act": 1, "out32": 1, "out16b": 1}),  # generic mode
+    # second (never row-scaled) bias of the residual epilogue: TMA epilogue (N % 32 == 0) and the generic one
+    (3 * 17 + 300, 768, 768, 0, 0, torch.float16, {"bias": 1, "bias2": 1, "resid": 1, "skip": 17, "out32": 1, "rs": 1}),
+    (200, 296, 104, 0, 0, torch.float16, {"bias": 1, "bias2": 1, "resid": 1, "skip": 7, "out32": 1}),
 ]
 
 
@@ -63,9 +66,15 @@ def test_gemm16(case):
     Bm = b.float() if bl == 0 else b.float().t()
     ref = A @ Bm.t()
     kw = {}
+    if ex.get("rs"):    # DropPath-style row factors on the accumulator and on the first bias
+        kw["row_scale"] = (torch.rand(M, device=DEV, generator=gen) > 0.3).float() / 0.7
+        ref = ref * kw["row_scale"][:, None]
     if ex.get("bias"):
         kw["bias"] = torch.randn(N, device=DEV, generator=gen)
-        ref = ref + kw["bias"]
+        ref = ref + (kw["bias"] * kw["row_scale"][:, None] if ex.get("rs") else kw["bias"])
+    if ex.get("bias2"):
+        kw["bias2"] = torch.randn(N, device=DEV, generator=gen)
+        ref = ref + kw["bias2"]
     pre = ref.clone()
     act = ex.get("act", 0)
     if act == 1:

@@ -214,3 +214,47 @@ def test_prefetch_loader_matches_plain_copies():
         assert torch.equal(b["text_input_ids"].cpu(), h["text_input_ids"])
         n += 1
     assert n == 4
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_fused_temporal_fc_matches_two_linears(train, monkeypatch):
+    """ALPRO_FUSE_TFC=1 runs temporal_attn.proj -> DropPath -> temporal_fc (vit.py:157-161) as ONE GEMM with the composed
+    weight W_fc W_proj (second, unscaled bias b_fc; gradients un-composed by two d x d GEMMs). Same losses and the same
+    parameter gradients as the two-Linear path, in eval mode and with the DropPath draws of train mode replayed."""
+    cfg = configs.GOLDEN["tiny_retrieval"]
+    spec, sd, batch = helpers.make_inputs(cfg)
+    results = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ALPRO_FUSE_TFC", flag)
+        model = build_cuda_model(cfg, sd)
+        if train:
+            model.train()
+            torch.manual_seed(1234)          # same DropPath / dropout draws in both runs
+            torch.cuda.manual_seed_all(1234)
+            if hasattr(model.engine, "seed"):
+                model.engine.seed = 77
+        out = model(to_cuda(batch))
+        loss = out["itc_loss"] + out["itm_loss"]
+        loss.backward()
+        torch.cuda.synchronize()
+        results[flag] = ({k: out[k].detach().float().cpu() for k in ("itc_loss", "itm_loss", "itm_scores")},
+                         {n: p.grad.detach().float().cpu() for n, p in model.named_parameters() if p.grad is not None})
+    o0, g0 = results["0"]
+    o1, g1 = results["1"]
+    for k in o0:
+        assert helpers.rel_err(o1[k], o0[k]) < FWD_TOL, k
+    assert set(g0) == set(g1)
+    # the composition only touches the visual encoder; gradients that are pure rounding noise in both runs (e.g. the
+    # attention key biases, whose exact gradient is zero) are skipped by a floor relative to the largest gradient
+    floor = 1e-4 * max(float(t.double().norm()) for t in g0.values())
+    dev = []
+    for n in g0:
+        ref = float(g0[n].double().norm())
+        if ref < floor or "visual_encoder" not in n:
+            continue
+        dev.append((float((g1[n].double() - g0[n].double()).norm()) / ref, n))
+    dev.sort(reverse=True)
+    assert len(dev) > 20
+    print("fused temporal_fc: largest gradient deviations", [(n, f"{e:.2e}") for e, n in dev[:6]])
+    print("losses", {k: (float(o0[k].flatten()[0]), float(o1[k].flatten()[0])) for k in o0})
+    assert dev[0][0] < GRAD_TOL, dev[:6]
