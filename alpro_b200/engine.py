@@ -226,6 +226,47 @@ class VisualEncoder:
         return dict(rs_t=rs_t, rsa=rsa, rsb=rsb, rs_m=rs_m, m_s=m_s.reshape(-1).contiguous(),
                     cls_w=(m_s / T).reshape(-1).contiguous(), raw=dict(m_t=m_t, m_s=m_s, m_m=m_m))
 
+    def _drop_path_all(self, rate, B, N, T, dev, raw=None):
+        """The stochastic-depth factors of ALL blocks from one batched draw: the per-block version above costs ~13 tiny
+        launches per block (bernoulli / div / cat / copies), ~140 per training step; this one ~20 per step. Returns a list
+        with one dict (same keys as _drop_path_scales) or None per block. `raw` (tests): per-block (m_t, m_s, m_m) masks
+        already divided by keep, or None for blocks without DropPath, instead of a fresh draw."""
+        depth = self.depth
+        ps = [rate * i / max(depth - 1, 1) for i in range(depth)]
+        active = [i for i in range(depth) if ps[i] > 0.0]
+        out = [None] * depth
+        if not active:
+            return out
+        A, Sc = len(active), 1 + N * T
+        if raw is None:
+            ck = (rate, depth, str(dev))
+            if getattr(self, "_dp_keep_key", None) != ck:   # per-block keep probabilities, uploaded once
+                self._dp_keep = torch.tensor([1.0 - ps[i] for i in active], device=dev).view(A, 1, 1)
+                self._dp_keep_key = ck
+            keep = self._dp_keep
+            m = (torch.rand(A, B, N + T + 1, device=dev) < keep).float() / keep
+            m_t, m_s, m_m = m[:, :, :N], m[:, :, N:N + T], m[:, :, N + T]
+        else:
+            m_t = torch.stack([raw[i][0] for i in active])
+            m_s = torch.stack([raw[i][1] for i in active])
+            m_m = torch.stack([raw[i][2] for i in active])
+        rs_t = torch.zeros(A, B, Sc, device=dev)
+        rs_t[:, :, 1:] = m_t.unsqueeze(-1).expand(A, B, N, T).reshape(A, B, N * T)
+        sp = m_s.unsqueeze(2).expand(A, B, N, T).reshape(A, B, N * T)
+        rsa = torch.ones(A, B, Sc, device=dev)
+        rsa[:, :, 1:] = sp
+        rsb = torch.empty(A, B, Sc, device=dev)
+        rsb[:, :, 0] = m_s.mean(dim=2)
+        rsb[:, :, 1:] = sp
+        rs_m = m_m.unsqueeze(-1).expand(A, B, Sc).contiguous()
+        m_s_c = m_s.contiguous()
+        cls_w = m_s_c / T
+        for a, i in enumerate(active):
+            out[i] = dict(rs_t=rs_t[a].reshape(-1), rsa=rsa[a].reshape(-1), rsb=rsb[a].reshape(-1),
+                          rs_m=rs_m[a].reshape(-1), m_s=m_s_c[a].reshape(-1), cls_w=cls_w[a].reshape(-1),
+                          raw=dict(m_t=m_t[a], m_s=m_s[a], m_m=m_m[a]))
+        return out
+
     def forward(self, P, W, frames, save, drop_path_rate=0.0):
         """frames fp32 [B,T,3,H,W] -> video_embeds fp32 [B, 1+N, d]; ctx holds what the backward needs.
         drop_path_rate > 0 enables train-mode stochastic depth."""
@@ -271,11 +312,12 @@ class VisualEncoder:
         fuse_tfc = os.environ.get("ALPRO_FUSE_TFC", "1") != "0"
         if save:
             ctx["fuse_tfc"] = fuse_tfc
+        dps = self._drop_path_all(drop_path_rate, B, N, T, dev) if drop_path_rate > 0 else [None] * self.depth
         for i in range(self.depth):
             b = f"{p}blocks.{i}."
             g = lambda n: P[b + n].detach()
             w = lambda n: W.get(b + n, P[b + n])
-            dp = self._drop_path_scales(i, drop_path_rate, B, N, T, dev) if drop_path_rate > 0 else None
+            dp = dps[i]
             # ---- temporal attention branch (vit.py:146-162)
             a_t = buf("a_t", (M, d), dt)
             st_t = buf("st_t", (2, M), torch.float32)
@@ -367,9 +409,10 @@ class VisualEncoder:
         scratch = _empty((B * T, 3 * d), torch.float32, dev)
         ones_rows = None
         if ctx.get("fuse_tfc"):
-            dwc32 = _empty((d, d), torch.float32, dev)
+            # per-block accumulators of the composed-weight gradient, zeroed by two fills instead of two per block
+            dwc32_all = torch.zeros(self.depth, d, d, device=dev)
+            v32_all = torch.zeros(self.depth, d, device=dev)
             dwc16 = _empty((d, d), dt, dev)
-            v32 = torch.zeros(d, device=dev)
             ws = 256.0
 
         def wgrad(dy16, x16, wname, bname=None, zero_period=0):
@@ -418,7 +461,7 @@ class VisualEncoder:
                 # dWc = (s * d_res)^T o_t, kept at ws x its true scale so that its 16-bit copy neither overflows (a weight
                 # gradient sums over all tokens: the loss scale S of the activation gradients would be too much) nor
                 # underflows; v = colsum(s * d_res) stays fp32 at the loss scale
-                dwc32.zero_()
+                dwc32, v32 = dwc32_all[i], v32_all[i]
                 ops.gemm16(dx16, c["o_t"], a_layout=MNMAJOR, b_layout=MNMAJOR, out32=dwc32, split_k=-1, alpha=ws * inv)
                 ops.colsum(dx16, v32, 1.0, 0)
                 ops.cast16(dwc32.view(-1), dwc16.view(-1))
@@ -430,7 +473,6 @@ class VisualEncoder:
                 ops.small_linear_bwd(v32.view(1, -1), d, None, g("temporal_attn.proj.bias").view(1, -1), d,
                                      P[b + "temporal_fc.weight"].detach(), G[b + "temporal_attn.proj.bias"].view(1, -1),
                                      d, True, G[b + "temporal_fc.weight"], None, True, 1, d, d, alpha=inv)
-                v32.zero_()
             else:
                 ops.layernorm_bwd(da, c["x1"], c["st_s"][0], c["st_s"][1], g("norm1.weight"), dx, 1, dx16=dx16,
                                   zero_period=Sc, dgamma=G[b + "norm1.weight"], dbeta=G[b + "norm1.bias"],
