@@ -90,6 +90,12 @@ class BucketedAllReduce:
         self._G = None
         return self.bytes
 
+    def abandon(self):
+        """Join the side stream and forget the pending store (its p.grad tensors were reduced another way)."""
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self._G = None
+
 
 def attach(model, group=None, overlap=True):
     """Make `model` exchange VTC features across the ranks of `group` and (overlap=True) average its gradients while
@@ -105,13 +111,31 @@ def allreduce_gradients(model, group=None):
     """Average all parameter gradients across ranks. With comm.attach(model, overlap=True) most of the buffer has already
     been reduced on the side stream during backward and only the tail + stream join happen here; otherwise one collective
     over the flat gradient buffer."""
+    world = dist.get_world_size(group)
+    if not getattr(model, "_grads_aliased", True):
+        # p.grad was assigned by hand and does not alias the flat store: reduce the p.grad tensors themselves
+        gs = [p.grad for p in model.parameters() if p.grad is not None]
+        if not gs:
+            raise RuntimeError("no gradients to reduce: run loss.backward() first")
+        flat = torch.cat([g.reshape(-1) for g in gs])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        o = 0
+        for g in gs:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
+        red = getattr(model, "_grad_reducer", None)
+        if red is not None and red._G is not None:
+            red.abandon()
+        return flat.numel() * 4
     red = getattr(model, "_grad_reducer", None)
-    if red is not None and red._G is not None:
-        return red.finish()
+    if red is not None:
+        # overlap=True: everything but the tail was reduced during backward; nothing pending = already reduced
+        # (gradient accumulation joins each micro-step's reduction inside backward, modeling._publish_grads)
+        return red.finish() if red._G is not None else 0
     flat = getattr(model.engine, "last_grads", None)
     if flat is None:
         raise RuntimeError("no gradients to reduce: run loss.backward() first")
-    world = dist.get_world_size(group)
     if dist.get_backend(group) == "gloo":
         dist.all_reduce(flat.flat, op=dist.ReduceOp.SUM, group=group)
         flat.flat.div_(world)

@@ -32,11 +32,23 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
 // adamw.py:73-98:  m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= step_size * m / (sqrt(v) + eps) ;
 //                  p -= lr*wd * p   (decoupled decay applied to the already-updated p, :96-98)
 // g is first scaled by the clip coefficient min(1, max_norm / (||g|| + 1e-6)) when max_norm > 0.
+__global__ void adamw_prepare_kernel(const float* __restrict__ gnorm_sq, float lr, float beta1, float beta2,
+                                     int correct_bias, int* __restrict__ step_count, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (!isfinite(*gnorm_sq)) { *out = 0.f; return; }
+  const int t = ++*step_count;
+  float ss = lr;
+  if (correct_bias) ss = lr * sqrtf(1.f - powf(beta2, static_cast<float>(t))) / (1.f - powf(beta1, static_cast<float>(t)));
+  *out = ss;
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float beta1, float beta2, float eps, float step_size,
-                             float lr_wd, const float* __restrict__ gnorm_sq, float max_norm) {
+                             const float* __restrict__ step_size_dev, float lr_wd, const float* __restrict__ gnorm_sq,
+                             float max_norm) {
   float clip = 1.f;
   if (gnorm_sq && !isfinite(*gnorm_sq)) return;   // fp16 gradient overflow: skip this update (dynamic loss scaling)
+  if (step_size_dev) step_size = *step_size_dev;
   if (max_norm > 0.f && gnorm_sq) {
     const float c = max_norm / (sqrtf(*gnorm_sq) + 1e-6f);
     clip = c < 1.f ? c : 1.f;
@@ -86,8 +98,31 @@ extern "C" int alpro_adamw_step(float* p, const float* g, float* m, float* v, in
   long long gr = cdiv(n / 4, 256);
   if (gr > num_sms() * 8) gr = num_sms() * 8;
   adamw_kernel<<<static_cast<unsigned>(gr), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
-                                                                                        step_size, lr_wd, gnorm_sq,
-                                                                                        max_norm);
+                                                                                        step_size, nullptr, lr_wd,
+                                                                                        gnorm_sq, max_norm);
   ALPRO_CHECK_LAUNCH("alpro_adamw_step");
+  return 0;
+}
+
+extern "C" int alpro_adamw_prepare(const float* gnorm_sq, float lr, float beta1, float beta2, int correct_bias,
+                                   int* step_count, float* step_size_out, void* stream) {
+  ALPRO_REQUIRE(gnorm_sq && step_count && step_size_out, "alpro_adamw_prepare: bad args");
+  adamw_prepare_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(gnorm_sq, lr, beta1, beta2, correct_bias,
+                                                                       step_count, step_size_out);
+  ALPRO_CHECK_LAUNCH("alpro_adamw_prepare");
+  return 0;
+}
+
+extern "C" int alpro_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
+                                    float eps, const float* step_size_dev, float lr_wd, const float* gnorm_sq,
+                                    float max_norm, void* stream) {
+  ALPRO_REQUIRE(p && g && m && v && step_size_dev && n > 0 && (n % 4) == 0, "alpro_adamw_step_dev: bad args");
+  ALPRO_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "alpro_adamw_step_dev: alignment");
+  long long gr = cdiv(n / 4, 256);
+  if (gr > num_sms() * 8) gr = num_sms() * 8;
+  adamw_kernel<<<static_cast<unsigned>(gr), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
+                                                                                        0.f, step_size_dev, lr_wd,
+                                                                                        gnorm_sq, max_norm);
+  ALPRO_CHECK_LAUNCH("alpro_adamw_step_dev");
   return 0;
 }

@@ -25,7 +25,15 @@ def _empty(shape, dtype, dev):
 
 
 class OperandCache:
-    """16-bit operand copies of fp32 parameters, refreshed when a parameter's version counter changes."""
+    """16-bit operand copies of fp32 parameters.
+
+    A copy is refreshed when the parameter's version counter changes OR when the cache epoch has moved. The version
+    counter alone is not enough: optimizers that update through `p.data` (the reference's AdamW,
+    src/optimization/adamw.py:80-98, EMA / `p.data.copy_()` patterns) leave `_version` untouched. AlproEngine therefore
+    bumps the epoch at the start of every gradient-tracking forward and at the end of every backward, so each training
+    step re-casts its operands exactly once (~1.4 GB of traffic, ~0.3 ms) and an eval forward after a training step
+    never sees stale weights. Only repeated no-grad forwards reuse the copies; after an out-of-band `.data` update
+    between two no-grad forwards call `model.invalidate_operands()`."""
 
     def __init__(self, dtype):
         self.dtype = dtype
@@ -33,7 +41,8 @@ class OperandCache:
         self._epoch = 0
 
     def _key(self, ps):
-        return tuple((p.data_ptr(), p._version, self._epoch) for p in ps)
+        # frozen parameters (the pretraining teacher) are never touched by an optimizer: version counter only
+        return tuple((p.data_ptr(), p._version, self._epoch if p.requires_grad else -1) for p in ps)
 
     def invalidate(self):
         """Force a refresh of every operand copy (used after an out-of-band parameter update, e.g. FusedAdamW)."""
@@ -748,6 +757,8 @@ class AlproEngine:
         cfg, h, d = self.cfg, self.cfg["hidden_size"], self.vis["d"]
         save = need_grad
         comm = self.comm
+        if need_grad:
+            self.W.invalidate()      # a training step never trusts operand copies made before it (see OperandCache)
         ops.clamp_scalar(P["temp"].detach(), 0.001, 0.5)                       # temp.clamp_ :80-81 / :734-735
         frames = batch["visual_inputs"]
         B = frames.shape[0]
@@ -985,6 +996,7 @@ class AlproEngine:
         self.visual.backward(P, self.W, ctx["vctx"], dve, G, S, hook)
         if hook is not None:
             hook(G, G.flat.numel())
+        self.W.invalidate()          # an optimizer step (possibly through p.data) follows: next forward re-casts
         return G
 
     def _mlm_backward(self, P, ctx, G, gptr, dfo):

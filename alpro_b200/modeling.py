@@ -32,10 +32,28 @@ def _cfg_dict(config):
 def _vis_from_cfg(video_enc_cfg, d=768, depth=12, heads=12):
     """TimeSformer dims are hard-coded in the reference (vit.py:445-462); optional keys allow the small parity
     configuration (embed_dim/depth/num_heads)."""
-    return dict(d=video_enc_cfg.get("embed_dim", d), depth=video_enc_cfg.get("depth", depth),
-                heads=video_enc_cfg.get("num_heads", heads), T=video_enc_cfg["num_frm"],
-                img=video_enc_cfg["img_size"], patch=video_enc_cfg["patch_size"],
-                drop_path_rate=float(video_enc_cfg.get("drop_path_rate", 0.0)))
+    vis = dict(d=video_enc_cfg.get("embed_dim", d), depth=video_enc_cfg.get("depth", depth),
+               heads=video_enc_cfg.get("num_heads", heads), T=video_enc_cfg["num_frm"],
+               img=video_enc_cfg["img_size"], patch=video_enc_cfg["patch_size"],
+               drop_path_rate=float(video_enc_cfg.get("drop_path_rate", 0.0)))
+    # ImageNorm constants of the uint8 input path (config img_pixel_mean / img_pixel_std, e.g.
+    # config_release/msrvtt_ret.json:19-20; the trainer passes them to ImageNorm, src/datasets/data_utils.py:437-457)
+    if "img_pixel_mean" in video_enc_cfg:
+        vis["img_mean"] = tuple(float(v) for v in video_enc_cfg["img_pixel_mean"])
+    if "img_pixel_std" in video_enc_cfg:
+        vis["img_std"] = tuple(float(v) for v in video_enc_cfg["img_pixel_std"])
+    return vis
+
+
+def _default_dtype():
+    """ALPRO_DTYPE=bf16|fp16 selects the operand format of newly built models (default fp16)."""
+    import os
+    v = os.environ.get("ALPRO_DTYPE", "fp16").lower()
+    if v in ("bf16", "bfloat16"):
+        return torch.bfloat16
+    if v in ("fp16", "float16", "half"):
+        return torch.float16
+    raise ValueError(f"ALPRO_DTYPE={v!r}: expected fp16 or bf16")
 
 
 class _Holder(nn.Module):
@@ -113,10 +131,7 @@ class _StepFn(torch.autograd.Function):
         named = [(n, p) for n, p in zip(c["names"], c["params"]) if p.requires_grad]
         G = model.engine.backward(P, ctx.ectx, named, g)
         ctx.ectx = None
-        out = []
-        for n in ctx.names:
-            out.append(G[n] if n in G else None)
-        return (None, None, None, None) + tuple(out)
+        return (None, None, None, None) + model._publish_grads(G, ctx.names, named)
 
 
 class AlproBaseModel(nn.Module):
@@ -141,8 +156,21 @@ class AlproBaseModel(nn.Module):
         _init_like_reference(self)
         with torch.no_grad():
             self.temp.fill_(temp)
-        self.engine = AlproEngine(self.kind, self._cfg, self._vis, num_entities=self._cfg.get("num_entities"))
+        self.engine = AlproEngine(self.kind, self._cfg, self._vis, dtype=_default_dtype(),
+                                  num_entities=self._cfg.get("num_entities"))
         self._last_out = None
+
+    def set_compute_dtype(self, dtype, loss_scale=4096.0):
+        """GEMM operand / saved-activation format: torch.float16 (default; backward carries a static loss scale) or
+        torch.bfloat16 (no loss scale). Accumulation, residual stream and statistics are fp32 in both."""
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("compute dtype must be torch.float16 or torch.bfloat16")
+        old = self.engine
+        self.engine = AlproEngine(self.kind, self._cfg, self._vis, dtype=dtype, loss_scale=loss_scale,
+                                  num_entities=self._cfg.get("num_entities"))
+        self.engine.sampler, self.engine.comm = old.sampler, old.comm
+        self.engine.grad_ready_hook = old.grad_ready_hook
+        return self
 
     # ---- plumbing
     # Name -> tensor maps are built once and reused every step (walking named_parameters()/state_dict() cost ~19 ms of
@@ -176,6 +204,52 @@ class AlproBaseModel(nn.Module):
 
     def _tensor_dict(self):
         return self._param_cache()["tensors"]
+
+    def set_image_norm(self, mean, std):
+        """ImageNorm constants (img_pixel_mean / img_pixel_std of the task config) for raw uint8 `visual_inputs`."""
+        self._vis["img_mean"] = tuple(float(v) for v in mean)
+        self._vis["img_std"] = tuple(float(v) for v in std)
+        for enc in (self.engine.visual, getattr(self.engine, "t_visual", None)):
+            if enc is not None:
+                enc.img_mean, enc.img_std = self._vis["img_mean"], self._vis["img_std"]
+        return self
+
+    def invalidate_operands(self):
+        """Drop the 16-bit operand copies (needed only after an out-of-band `.data` update between two no-grad
+        forwards; training steps refresh them by themselves)."""
+        self.engine.W.invalidate()
+
+    def _publish_grads(self, G, names, named):
+        """Hand the flat gradient store of one backward pass to autograd.
+
+        First backward after `p.grad = None` (the reference trainers' zero_none_grad / set_to_none): the returned views
+        become `p.grad`, so `p.grad` ALIASES `engine.last_grads.flat` — the buffer comm.allreduce_gradients and
+        FusedAdamW work on. Gradient accumulation (`gradient_accumulation_steps` > 1, or `zero_grad(set_to_none=False)`):
+        `p.grad` still aliases the store of the first micro-step, so the new store is added into it with ONE flat add
+        (after its own overlapped all-reduce, if any, has been joined: averaging is linear) and that accumulated store
+        stays `engine.last_grads`. A `p.grad` that does not alias our store (assigned by hand) falls back to autograd's
+        per-tensor accumulation and is flagged, so that allreduce_gradients reduces the `p.grad` tensors themselves."""
+        eng = self.engine
+        acc = getattr(eng, "grad_accum", None)
+        live = [(n, p) for n, p in named if p.grad is not None]
+        if not live:
+            eng.grad_accum = eng.last_grads = G
+            self._grads_aliased = True
+            return tuple(G[n] if n in G else None for n in names)
+        aliased = (acc is not None and acc.offsets == G.offsets and acc.flat.device == G.flat.device
+                   and len(live) == len(named)
+                   and all(p.grad.data_ptr() == acc[n].data_ptr() for n, p in named))
+        if aliased:
+            red = getattr(self, "_grad_reducer", None)
+            if red is not None and red._G is G:
+                red.finish()
+            acc.flat.add_(G.flat)
+            eng.last_grads = acc
+            self._grads_aliased = True
+            return tuple(None for _ in names)
+        self._grads_aliased = False
+        eng.grad_accum = None
+        return tuple(G[n] if n in G else None for n in names)
 
     def _check_device(self, batch):
         v = batch["visual_inputs"]

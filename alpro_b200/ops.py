@@ -366,3 +366,13 @@ def sumsq(x, out):
 def adamw_step(p, g, m, v, beta1, beta2, eps, step_size, lr_wd, gnorm_sq, max_norm):
     check(_L.alpro_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), beta1, beta2, eps, step_size, lr_wd,
                               _p(gnorm_sq), max_norm, _s()), "alpro_adamw_step")
+
+
+def adamw_prepare(gnorm_sq, lr, beta1, beta2, correct_bias, step_count, step_size_out):
+    check(_L.alpro_adamw_prepare(_p(gnorm_sq), lr, beta1, beta2, int(correct_bias), _p(step_count), _p(step_size_out),
+                                 _s()), "alpro_adamw_prepare")
+
+
+def adamw_step_dev(p, g, m, v, beta1, beta2, eps, step_size_dev, lr_wd, gnorm_sq, max_norm):
+    check(_L.alpro_adamw_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), beta1, beta2, eps, _p(step_size_dev), lr_wd,
+                                  _p(gnorm_sq), max_norm, _s()), "alpro_adamw_step_dev")

@@ -4,8 +4,6 @@ Replaces `clip_grad_norm_(...)` + `AdamW.step()` of the reference trainers (run_
 src/optimization/adamw.py:40-103) with two kernel launches over flat fp32 buffers. The parameters of the model are
 re-pointed to views of one flat buffer laid out exactly like the engine's GradStore, so `grad`, `exp_avg`, `exp_avg_sq`
 and the parameters are element-aligned."""
-import math
-
 import torch
 
 from . import ops
@@ -34,25 +32,25 @@ class FusedAdamW:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
-        self.step_count = 0
+        # number of updates actually applied, kept on the device: a step the kernel skips (non-finite gradient norm
+        # after an fp16 overflow) does not advance the bias-correction schedule
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.step_size_dev = torch.zeros(1, device=dev, dtype=torch.float32)
 
     def step(self):
         G = self.model.engine.last_grads
         if G is None:
             raise RuntimeError("FusedAdamW.step(): run loss.backward() first")
         assert G.offsets == self.offsets, "gradient layout changed"
-        self.step_count += 1
         b1, b2 = self.betas
-        step_size = self.lr
-        if self.correct_bias:
-            step_size = step_size * math.sqrt(1.0 - b2 ** self.step_count) / (1.0 - b1 ** self.step_count)
         # the squared gradient norm is always computed: it drives clipping and makes the kernel skip the update when the
         # fp16 backward overflowed (non-finite norm)
         self.gnorm_sq.zero_()
         ops.sumsq(G.flat, self.gnorm_sq)
         clip = self.max_grad_norm if (self.max_grad_norm is not None and self.max_grad_norm > 0) else -1.0
-        ops.adamw_step(self.flat, G.flat, self.exp_avg, self.exp_avg_sq, b1, b2, self.eps, step_size,
-                       self.lr * self.wd, self.gnorm_sq, clip)
+        ops.adamw_prepare(self.gnorm_sq, self.lr, b1, b2, self.correct_bias, self.step_dev, self.step_size_dev)
+        ops.adamw_step_dev(self.flat, G.flat, self.exp_avg, self.exp_avg_sq, b1, b2, self.eps, self.step_size_dev,
+                           self.lr * self.wd, self.gnorm_sq, clip)
         self.model.engine.W.invalidate()     # 16-bit operand copies are stale now
 
     def update_loss_scale(self, growth_interval=1000):
@@ -68,6 +66,11 @@ class FusedAdamW:
                 eng.S *= 2.0
                 self._good = 0
         return eng.S
+
+    @property
+    def step_count(self):
+        """Updates applied so far (host sync)."""
+        return int(self.step_dev.item())
 
     def grad_norm(self):
         """sqrt of the last computed squared gradient norm (device tensor; no sync)."""

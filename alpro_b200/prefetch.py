@@ -3,12 +3,14 @@
 Mirrors the reference's PrefetchLoader (src/datasets/dataloader.py:80-157): iterate an inner loader of (pinned) host
 batches, copy the NEXT batch on a dedicated CUDA stream while the current one is consumed, make the compute stream wait
 for that copy before handing the batch out, and record the tensors on the compute stream so the caching allocator does
-not recycle them early. Differences: the copies land in two preallocated device staging sets that are reused
-alternately (no per-step cudaMalloc / allocator traffic on the side stream; the reference's commented-out
+not recycle them early. Differences: the copies land in three preallocated device staging sets that are reused
+in rotation (no per-step cudaMalloc / allocator traffic on the side stream; the reference's commented-out
 "alternative if record_stream() doesn't work"); frames may stay uint8 (alpro_b200 fuses ImageNorm into its patch gather, so the
 4x smaller uint8 clip is what crosses PCIe); `img_normalize`, when given, is applied on the side stream as in the
-reference (after `.float()`). A batch stays valid until the loader has been advanced twice more (its staging set is
-then overwritten), which is the life time a training step needs.
+reference (after `.float()`). Life time of a batch: three staging sets rotate, and fetching batch i+1 stages batch
+i+2, so batch i is overwritten by the copy issued when batch i+2 is FETCHED (that copy is stream-ordered after
+everything enqueued on the compute stream before the fetch). A trainer may therefore still use the previous batch
+while working on the current one, but nothing older; clone what must live longer.
 """
 import torch
 
@@ -34,7 +36,7 @@ class PrefetchLoader:
         self.img_normalize = img_normalize
         self.stream = torch.cuda.Stream(device=self.device)
         self.batch = None
-        self._ring = [{}, {}]   # two staging sets: path -> device tensor
+        self._ring = [{}, {}, {}]   # three staging sets: path -> device tensor
         self._slot = 0
 
     def _stage(self, obj, ring, path=""):
@@ -64,14 +66,14 @@ class PrefetchLoader:
         except StopIteration:
             self.batch = None
             return
-        # the staging set about to be overwritten was handed out two batches ago: the copy may start once the compute
+        # the staging set about to be overwritten was handed out three batches ago: the copy may start once the compute
         # stream has finished what it has been given so far (the consumer has not enqueued the current step yet)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             is_tuple = isinstance(batch, tuple)
             task, body = batch if is_tuple else (None, batch)
             body = self._stage(body, self._ring[self._slot])
-            self._slot ^= 1
+            self._slot = (self._slot + 1) % len(self._ring)
             if self.img_normalize is not None and isinstance(body, dict):
                 for k in VISUAL_KEYS:
                     if k in body:

@@ -29,7 +29,7 @@ FLOP_PER_PAIR = {"pretrain": 1846.9e9, "retrieval": 1375.7e9}
 
 
 def full_cfg(kind):
-    from oracle import configs
+    from alpro_b200 import configs
     bert = dict(configs.BASE_BERT)
     video = dict(configs.BASE_VIDEO)
     video.update(num_frm=T_FRAMES, img_size=IMG)

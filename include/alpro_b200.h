@@ -236,6 +236,14 @@ int alpro_sumsq(const float* x, int64_t n, float* out, void* stream);
  * when max_norm > 0; step_size = lr*sqrt(1-b2^t)/(1-b1^t) (or lr without bias correction); lr_wd = lr*weight_decay */
 int alpro_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
                      float step_size, float lr_wd, const float* gnorm_sq, float max_norm, void* stream);
+/* Device-side step bookkeeping for alpro_adamw_step: when *gnorm_sq is finite, ++*step_count (the number of updates
+ * actually APPLIED; an fp16-overflow step is skipped and not counted) and *step_size_out = lr*sqrt(1-b2^t)/(1-b1^t)
+ * (lr when correct_bias == 0); otherwise *step_size_out = 0. Pass step_size_out as `step_size_dev` below. */
+int alpro_adamw_prepare(const float* gnorm_sq, float lr, float beta1, float beta2, int correct_bias, int* step_count,
+                        float* step_size_out, void* stream);
+/* alpro_adamw_step with the step size read from device memory (written by alpro_adamw_prepare) */
+int alpro_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                         const float* step_size_dev, float lr_wd, const float* gnorm_sq, float max_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,11 +100,43 @@ def vit_tokens(sd, p, frames, patch):
     return torch.cat([cls.expand(B, 1, d), y], dim=1)
 
 
+class RandomDrop:
+    """Train-mode regularisers drawn by torch at run time (timing legs of bench.py; parity tests inject masks instead):
+    hidden dropout p_hidden (xbert.py:178,358,436), attention-probability dropout p_attn (xbert.py:331)."""
+
+    def __init__(self, p_hidden, p_attn):
+        self.p_hidden, self.p_attn = p_hidden, p_attn
+
+
+def random_train(cfg, vis, drop_path_rate=0.1):
+    """`train=` argument that makes retrieval_forward / pretrain_forward draw their own masks (reference .train())."""
+    rd = {i: RandomDrop(cfg["hidden_dropout_prob"], cfg["attention_probs_dropout_prob"])
+          for i in range(cfg["num_hidden_layers"])}
+    return dict(drop_path=float(drop_path_rate), emb=float(cfg["hidden_dropout_prob"]), text=rd, pos=rd, neg=rd,
+                emb_mlm=float(cfg["hidden_dropout_prob"]), text_mlm=rd, mlm=rd)
+
+
+def _random_drop_path(rate, depth, B, N, T, dev):
+    """DropPath draws of every block (vit_utils.py:137-162; rate scaled linearly over depth, vit.py:272-277)."""
+    out = []
+    for i in range(depth):
+        pr = rate * i / max(depth - 1, 1)
+        if pr <= 0:
+            out.append(None)
+            continue
+        keep = 1.0 - pr
+        draw = lambda *shape: torch.bernoulli(torch.full(shape, keep, device=dev)) / keep
+        out.append(dict(m_t=draw(B, N), m_s=draw(B, T), m_m=draw(B)))
+    return out
+
+
 def visual_forward(sd, p, frames, vis, return_tokens=False, drop_path=None):
     """TimeSformer.forward_features vit.py:475-503 (pooling='temporal'): blocks, final LN (vit.py:372), mean over t.
     p is the prefix of the VisionTransformer ('visual_encoder.model.'). Returns [B, 1+N, d]."""
     B, T = frames.shape[:2]
     x = vit_tokens(sd, p, frames, vis["patch"])
+    if isinstance(drop_path, float):
+        drop_path = _random_drop_path(drop_path, vis["depth"], B, (x.shape[1] - 1) // T, T, x.device)
     for i in range(vis["depth"]):
         x = vit_block(sd, f"{p}blocks.{i}.", x, B, T, vis["heads"], dp=drop_path[i] if drop_path else None)
     d = x.shape[-1]
@@ -127,6 +159,8 @@ def bert_embeddings(sd, p, ids, eps, mask=None):
         + sd[e + "position_embeddings.weight"][:L].unsqueeze(0)
     h = x.shape[-1]
     y = F.layer_norm(x, (h,), sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], eps)
+    if isinstance(mask, float):
+        return F.dropout(y, mask, True)
     return y if mask is None else y * mask.reshape(y.shape)
 
 
@@ -141,16 +175,23 @@ def bert_layer(sd, l, x, ext_mask, heads, eps, drop=None):
     q, k, v = proj("query"), proj("key"), proj("value")
     scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh) + ext_mask           # xbert.py:317-320
     probs = torch.softmax(scores, dim=-1)
-    if drop is not None and len(drop) > 2 and drop[2] is not None:
+    rnd = isinstance(drop, RandomDrop)
+    if rnd:
+        probs = F.dropout(probs, drop.p_attn, True)
+    elif drop is not None and len(drop) > 2 and drop[2] is not None:
         probs = probs * drop[2]                                             # attention_probs dropout, xbert.py:331
     ctx = (probs @ v).transpose(1, 2).reshape(Bp, S, h)
     a = F.linear(ctx, sd[l + "attention.output.dense.weight"], sd[l + "attention.output.dense.bias"])
-    if drop is not None:
+    if rnd:
+        a = F.dropout(a, drop.p_hidden, True)
+    elif drop is not None:
         a = a * drop[0].reshape(a.shape)                                    # BertSelfOutput.dropout, xbert.py:358
     a = F.layer_norm(a + x, (h,), sd[l + "attention.output.LayerNorm.weight"], sd[l + "attention.output.LayerNorm.bias"], eps)
     i = F.gelu(F.linear(a, sd[l + "intermediate.dense.weight"], sd[l + "intermediate.dense.bias"]))
     o = F.linear(i, sd[l + "output.dense.weight"], sd[l + "output.dense.bias"])
-    if drop is not None:
+    if rnd:
+        o = F.dropout(o, drop.p_hidden, True)
+    elif drop is not None:
         o = o * drop[1].reshape(o.shape)                                    # BertOutput.dropout, xbert.py:436
     return F.layer_norm(o + a, (h,), sd[l + "output.LayerNorm.weight"], sd[l + "output.LayerNorm.bias"], eps)
 
@@ -198,7 +239,7 @@ def vtc(sd, pfx, video_cls, text_cls, rank=0, gather=None):
     sim_v2t = vf @ gt.t() / temp
     sim_t2v = tf @ gv.t() / temp
     b = vf.shape[0]
-    tgt = torch.arange(b) + b * rank                                       # sim_targets block, :119-123
+    tgt = torch.arange(b, device=vf.device) + b * rank                     # sim_targets block, :119-123
     loss = 0.5 * (F.cross_entropy(sim_v2t, tgt) + F.cross_entropy(sim_t2v, tgt))
     return loss, sim_v2t, sim_t2v, vf, tf
 
@@ -222,9 +263,10 @@ def vtm(sd, pfx, cfg, text_embeds, text_mask, video_embeds, neg_video, neg_text,
     Returns loss, logits [3b,2], labels, positive fusion output [b, L+1+N, h]."""
     b, L = text_mask.shape
     nv = video_embeds.shape[1]
-    ones = torch.ones(b, nv, dtype=text_mask.dtype)
-    nvi = torch.tensor(neg_video, dtype=torch.long)
-    nti = torch.tensor(neg_text, dtype=torch.long)
+    dev = video_embeds.device
+    ones = torch.ones(b, nv, dtype=text_mask.dtype, device=dev)
+    nvi = torch.tensor(neg_video, dtype=torch.long, device=dev)
+    nti = torch.tensor(neg_text, dtype=torch.long, device=dev)
     emb_pos = torch.cat([text_embeds, video_embeds], dim=1)
     mask_pos = torch.cat([text_mask, ones], dim=1)
     out_pos = bert_encode(sd, pfx + "text_encoder.", emb_pos, mask_pos, cfg, "fusion", drops_pos)
@@ -236,7 +278,7 @@ def vtm(sd, pfx, cfg, text_embeds, text_mask, video_embeds, neg_video, neg_text,
     out_neg = bert_encode(sd, pfx + "text_encoder.", emb_neg, mask_neg, cfg, "fusion", drops_neg)
     cls = torch.cat([out_pos[:, 0], out_neg[:, 0]], dim=0)
     logits = F.linear(cls, sd[pfx + "itm_head.weight"], sd[pfx + "itm_head.bias"])
-    labels = torch.cat([torch.ones(b, dtype=torch.long), torch.zeros(2 * b, dtype=torch.long)])
+    labels = torch.cat([torch.ones(b, dtype=torch.long, device=dev), torch.zeros(2 * b, dtype=torch.long, device=dev)])
     return F.cross_entropy(logits, labels), logits, labels, out_pos
 
 
@@ -265,7 +307,7 @@ def inference_forward(sd, cfg, vis, batch):
     tf = F.normalize(F.linear(text_embeds[:, 0], sd["text_proj.weight"], sd["text_proj.bias"]), dim=-1)
     n = text_embeds.shape[0]
     ve = video_embeds.repeat(n, 1, 1)
-    mask = torch.cat([batch["text_input_mask"], torch.ones(ve.shape[:2], dtype=torch.long)], dim=1)
+    mask = torch.cat([batch["text_input_mask"], torch.ones(ve.shape[:2], dtype=torch.long, device=ve.device)], dim=1)
     out = bert_encode(sd, "text_encoder.", torch.cat([text_embeds, ve], dim=1), mask, cfg, "fusion")
     logits = F.linear(out[:, 0], sd["itm_head.weight"], sd["itm_head.bias"])
     return dict(logits=logits, itc_scores=vf @ tf.t() / temp)
@@ -284,25 +326,30 @@ def pseudo_labels(sd, cfg, vis, batch):
     return soft, ignore
 
 
-def pretrain_forward(sd, cfg, vis, batch, rank=0, gather=None, sampler=argmax_sampler):
-    """AlproForPretrain.forward alpro_models.py:79-183 (use_mask_prob = 0 so context_visual_inputs is unused)."""
+def pretrain_forward(sd, cfg, vis, batch, rank=0, gather=None, sampler=argmax_sampler, train=None):
+    """AlproForPretrain.forward alpro_models.py:79-183 (use_mask_prob = 0 so context_visual_inputs is unused).
+    `train` (tests only): injected regulariser masks as in retrieval_forward, plus the MLM branch's own draws:
+    emb_mlm / text_mlm (text pass over the masked ids, compute_mlm :352-356) and mlm (its fusion pass :358-364).
+    The teacher (Prompter.get_pseudo_labels :531-535) always runs in eval mode."""
     pfx = ""
-    video_embeds = visual_forward(sd, "visual_encoder.model.", batch["visual_inputs"], vis)
+    tr = train or {}
+    video_embeds = visual_forward(sd, "visual_encoder.model.", batch["visual_inputs"], vis, drop_path=tr.get("drop_path"))
     mask = batch["text_input_mask"]
-    text_embeds = bert_text(sd, "text_encoder.", batch["text_input_ids"], mask, cfg)
+    text_embeds = bert_text(sd, "text_encoder.", batch["text_input_ids"], mask, cfg, tr.get("emb"), tr.get("text"))
     itc_loss, s_v2t, s_t2v, vf, tf = vtc(sd, pfx, video_embeds[:, 0], text_embeds[:, 0], rank, gather)
     neg_v, neg_t = mine_negatives(s_v2t.detach(), s_t2v.detach(), rank, sampler)
-    itm_loss, itm_scores, itm_labels, out_pos = vtm(sd, pfx, cfg, text_embeds, mask, video_embeds, neg_v, neg_t)
+    itm_loss, itm_scores, itm_labels, out_pos = vtm(sd, pfx, cfg, text_embeds, mask, video_embeds, neg_v, neg_t,
+                                                    tr.get("pos"), tr.get("neg"))
     out = dict(itc_loss=itc_loss, itm_scores=itm_scores, itm_loss=itm_loss, itm_labels=itm_labels,
                mlm_scores=None, mlm_loss=None, mlm_labels=None, mpm_loss=None, mpm_logits=None, mpm_labels=None,
                _video_embeds=video_embeds, _text_embeds=text_embeds, _neg_video=neg_v, _neg_text=neg_t)
     b, L = mask.shape
     nv = video_embeds.shape[1]
-    ones = torch.ones(b, nv, dtype=mask.dtype)
+    ones = torch.ones(b, nv, dtype=mask.dtype, device=mask.device)
     if "mlm_labels" in batch:                                               # compute_mlm :346-373
-        mt = bert_text(sd, "text_encoder.", batch["mlm_text_input_ids"], mask, cfg)
+        mt = bert_text(sd, "text_encoder.", batch["mlm_text_input_ids"], mask, cfg, tr.get("emb_mlm"), tr.get("text_mlm"))
         fo = bert_encode(sd, "text_encoder.", torch.cat([mt, video_embeds], dim=1), torch.cat([mask, ones], dim=1),
-                         cfg, "fusion")
+                         cfg, "fusion", tr.get("mlm"))
         scores = mlm_head(sd, "text_encoder.", fo[:, :L], cfg["layer_norm_eps"])
         out["mlm_scores"] = scores
         out["mlm_labels"] = batch["mlm_labels"]

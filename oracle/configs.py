@@ -1,16 +1,7 @@
 """Parity-test configurations shared by oracle/make_golden.py and tests/. TEST INFRASTRUCTURE."""
 import copy
 
-BASE_BERT = {  # /root/reference/config_release/base_model.json
-    "attention_probs_dropout_prob": 0.1, "hidden_act": "gelu", "hidden_dropout_prob": 0.1, "hidden_size": 768,
-    "initializer_range": 0.02, "intermediate_size": 3072, "layer_norm_eps": 1e-12, "max_position_embeddings": 512,
-    "model_type": "bert", "num_attention_heads": 12, "num_hidden_layers": 12, "pad_token_id": 0,
-    "type_vocab_size": 2, "vocab_size": 30522, "fusion_layer": 6, "encoder_width": 768, "itc_token_type": "cls",
-}
-BASE_VIDEO = {  # /root/reference/config_release/timesformer_divst_8x32_224_k600.json
-    "cls": "TimeSformer", "patch_size": 16, "attn_drop_rate": 0, "drop_rate": 0, "drop_path_rate": 0.1,
-    "maxpool_kernel_size": 2, "use_maxpooling": False, "gradient_checkpointing": False,
-}
+from alpro_b200.configs import BASE_BERT, BASE_VIDEO  # noqa: E402,F401  (one statement of the released constants)
 
 
 def tiny(kind, B=2, T=2, img=64, L=8, d=192, depth=2, heads=3, bert_layers=4, fusion_layer=2, vocab=1000,

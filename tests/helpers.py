@@ -42,3 +42,55 @@ def rel_err(a, b):
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def collect_train_masks(model, cfg):
+    """Regulariser masks of the CUDA model's last train-mode forward (kept in the step context), reshaped for the
+    oracle's `train=` injection (oracle/alpro_oracle.py retrieval_forward / pretrain_forward). Call BEFORE backward:
+    the step context is released block by block."""
+    from alpro_b200 import ops
+    ctx = model.engine.last_ctx
+    B = cfg["B"]
+    tr = {"drop_path": [None if blk["dp"] is None else {k: v.cpu() for k, v in blk["dp"]["raw"].items()}
+                        for blk in ctx["vctx"]["blocks"]]}
+    h = cfg["bert"]["hidden_size"]
+    L, R = ctx["L"], ctx["R"]
+    nt, S_all = ctx["nt"], ctx["S_all"]
+    heads = cfg["bert"]["num_attention_heads"]
+    emb = ctx["ectx"]["mask"].float().cpu().view(-1, L, h)
+    tr["emb"] = emb[:B]
+    if nt > B:
+        tr["emb_mlm"] = emb[B:2 * B]
+
+    def amask(c, S, nseq):
+        if not c["pattn"]:
+            return None
+        m = torch.empty(nseq, heads, S, S, device="cuda")
+        ops.attn_dropout_mask(m, S, nseq, heads, c["pattn"], c["aseed"])
+        return m.cpu()
+
+    tr["text"], tr["text_mlm"] = {}, {}
+    for c in ctx["tctx"]["layers"]:
+        am = amask(c, L, nt)
+        mo, mf = c["mo"].float().cpu().view(-1, L, h), c["mf"].float().cpu().view(-1, L, h)
+        tr["text"][c["i"]] = (mo[:B], mf[:B], None if am is None else am[:B])
+        if nt > B:
+            tr["text_mlm"][c["i"]] = (mo[B:2 * B], mf[B:2 * B], None if am is None else am[B:2 * B])
+    tr["pos"], tr["neg"], tr["mlm"] = {}, {}, {}
+    for c in ctx["fctx"]["layers"]:
+        a, b = c["mo"].float().cpu().view(-1, R, h), c["mf"].float().cpu().view(-1, R, h)
+        am = amask(c, R, S_all)
+        tr["pos"][c["i"]] = (a[:B], b[:B], None if am is None else am[:B])
+        tr["neg"][c["i"]] = (a[B:3 * B], b[B:3 * B], None if am is None else am[B:3 * B])
+        if S_all > 3 * B:
+            tr["mlm"][c["i"]] = (a[3 * B:4 * B], b[3 * B:4 * B], None if am is None else am[3 * B:4 * B])
+    if nt == B:
+        for k in ("emb_mlm", "text_mlm", "mlm"):
+            tr.pop(k, None)
+    return tr

@@ -97,37 +97,7 @@ def test_layernorm_train_hooks(M):
 
 
 def _collect_train_masks(model, cfg):
-    """Regulariser masks of the last forward, reshaped for the oracle."""
-    ctx = model.engine.last_ctx
-    B = cfg["B"]
-    tr = {"drop_path": [None if blk["dp"] is None else {k: v.cpu() for k, v in blk["dp"]["raw"].items()}
-                        for blk in ctx["vctx"]["blocks"]]}
-    h = cfg["bert"]["hidden_size"]
-    L, R = ctx["L"], ctx["R"]
-    tr["emb"] = ctx["ectx"]["mask"].float().cpu().view(-1, L, h)[:B]
-    from alpro_b200 import ops
-    heads = cfg["bert"]["num_attention_heads"]
-
-    def amask(c, S, nseq):
-        if not c["pattn"]:
-            return None
-        m = torch.empty(nseq, heads, S, S, device="cuda")
-        ops.attn_dropout_mask(m, S, nseq, heads, c["pattn"], c["aseed"])
-        return m.cpu()
-
-    nt, S_all = ctx["nt"], ctx["S_all"]
-    tr["text"] = {}
-    for c in ctx["tctx"]["layers"]:
-        am = amask(c, L, nt)
-        tr["text"][c["i"]] = (c["mo"].float().cpu().view(-1, L, h)[:B], c["mf"].float().cpu().view(-1, L, h)[:B],
-                              None if am is None else am[:B])
-    tr["pos"], tr["neg"] = {}, {}
-    for c in ctx["fctx"]["layers"]:
-        a, b = c["mo"].float().cpu().view(-1, R, h), c["mf"].float().cpu().view(-1, R, h)
-        am = amask(c, R, S_all)
-        tr["pos"][c["i"]] = (a[:B], b[:B], None if am is None else am[:B])
-        tr["neg"][c["i"]] = (a[B:3 * B], b[B:3 * B], None if am is None else am[B:3 * B])
-    return tr
+    return helpers.collect_train_masks(model, cfg)
 
 
 def test_train_mode_step_matches_oracle_with_injected_masks():
