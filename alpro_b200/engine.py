@@ -738,6 +738,39 @@ class AlproEngine:
     def _text_mask_add(self, mask):
         return ((1.0 - mask.to(torch.float32)) * -10000.0).contiguous()
 
+    def clamp_temp(self, P):
+        ops.clamp_scalar(P["temp"].detach(), 0.001, 0.5)                       # temp.clamp_ :80-81 / :598-599 / :734-735
+
+    def text_features(self, P, ids, mask):
+        """No-grad text pass: (text_embeds [n,L,h], F.normalize(text_proj(cls)) [n,256]); alpro_models.py:196-207."""
+        ids, mask = ids.contiguous(), mask.contiguous()
+        n, L = ids.shape
+        h = self.cfg["hidden_size"]
+        x32, x16, _ = self.bert.embed(P, ids, False)
+        te, _, _ = self.bert.forward(P, self.W, x32, x16, self._text_mask_add(mask), n, L, "text", False)
+        tf, _ = self._proj_norm(P, te, L * h, "text_proj", n)
+        return te.view(n, L, h), tf
+
+    def visual_feat(self, P, frames):
+        """No-grad visual pass: (video_embeds [B,1+N,d], F.normalize(vision_proj(cls)) [B,256]); :509-523."""
+        ve, _ = self.visual.forward(P, self.W, frames, False)
+        vf, _ = self._proj_norm(P, ve, ve.shape[1] * self.vis["d"], "vision_proj", ve.shape[0])
+        return ve, vf
+
+    def pseudo_labels(self, P, frames, type_="video"):
+        """Prompter.get_pseudo_labels (alpro_models.py:531-551) for a Prompter-kind engine: softmax of the similarity
+        to the prompt features / temp; ignore iff the argmax INDEX < 0.2 (sic, :527)."""
+        B = frames.shape[0]
+        _, vf = self.visual_feat(P, frames)
+        prompt = P["video_prompt_feat"] if type_ == "video" else P["image_prompt_feat"]
+        E = prompt.shape[0]
+        sim = _empty((B, E), torch.float32, frames.device)
+        ops.small_linear_fwd(vf, 256, prompt.detach().contiguous(), None, sim, B, E, 256, 1.0, P["temp"].detach(), 2)
+        soft = _empty((B, E), torch.float32, frames.device)
+        ignore = _empty((B,), torch.uint8, frames.device)
+        ops.pseudo_labels(sim, soft, ignore)
+        return soft, ignore.bool()
+
     # ------------------------------------------------------------------------------------------------ forward
     def _seed_stream(self):
         """Python-side stream of 32-bit seeds for the dropout sites of one forward pass (no device sync)."""
@@ -787,17 +820,37 @@ class AlproEngine:
         # ---- VTC (alpro_models.py:103-128, 750-779)
         vf, vnorm = self._proj_norm(P, ve, Nv * d, "vision_proj", B)
         tf, tnorm = self._proj_norm(P, te, L * h, "text_proj", B)
-        gv, gt = comm.all_gather(vf), comm.all_gather(tf)
+        # ONE exchange for both feature sets (the reference issues two hvd.allgather calls, alpro_models.py:110-111):
+        # [B, 512] = video | text rows, gathered in rank order; gv / gt are strided views into the gathered buffer
+        if comm.world > 1:
+            gvt = comm.all_gather(torch.cat([vf, tf], dim=1))
+            gv, gt, ldg = gvt[:, :256], gvt[:, 256:], 512
+        else:
+            gv, gt, ldg = vf, tf, 256
         Gn = gv.shape[0]
         temp = P["temp"].detach()
         sim_v2t = _empty((B, Gn), torch.float32, dev)
         sim_t2v = _empty((B, Gn), torch.float32, dev)
-        ops.small_linear_fwd(vf, 256, gt, None, sim_v2t, B, Gn, 256, 1.0, temp, 2)
-        ops.small_linear_fwd(tf, 256, gv, None, sim_t2v, B, Gn, 256, 1.0, temp, 2)
+        ops.small_linear_fwd(vf, 256, gt, None, sim_v2t, B, Gn, 256, 1.0, temp, 2, ldw=ldg)
+        ops.small_linear_fwd(tf, 256, gv, None, sim_t2v, B, Gn, 256, 1.0, temp, 2, ldw=ldg)
         vtc_labels = torch.arange(B, device=dev, dtype=torch.int64) + B * comm.rank   # local_rank block :119-123
         ce_v = ops.softmax_ce_fwd(sim_v2t, Gn, hard=vtc_labels, denom_mode=1)
         ce_t = ops.softmax_ce_fwd(sim_t2v, Gn, hard=vtc_labels, denom_mode=1)
         itc_loss = (ce_v.loss + ce_t.loss) * 0.5
+
+        if kind == "prompter":
+            # Prompter.forward (alpro_models.py:553-595): the contrastive objective alone
+            out = dict(itc_loss=itc_loss, itc_labels=vtc_labels, i2t_scores=None, t2i_scores=None)
+            lsm_v = sim_v2t - ce_v.row_lse.view(B, 1)                          # F.log_softmax(sim, dim=1) :581-582
+            lsm_t = sim_t2v - ce_t.row_lse.view(B, 1)
+            out.update(i2t_scores=lsm_v, t2i_scores=lsm_t, _video_embeds=ve, _text_embeds=te[:B])
+            ctx = None
+            if save:
+                ctx = dict(B=B, L=L, Nv=Nv, nt=nt, ve=ve, te=te, vctx=vctx, ectx=ectx, tctx=tctx, vf=vf, vnorm=vnorm,
+                           tf=tf, tnorm=tnorm, gv=gv, gt=gt, sim_v2t=sim_v2t, sim_t2v=sim_t2v, ce_v=ce_v, ce_t=ce_t,
+                           vtc_labels=vtc_labels, use_mlm=False, use_mpm=False, vtc_only=True)
+            self.last_ctx = ctx
+            return out, ctx
 
         # ---- hard negatives (alpro_models.py:288-316)
         w_t2v = _empty((B, B), torch.float32, dev)
@@ -925,10 +978,12 @@ class AlproEngine:
         inv = 1.0 / S
         dev = ctx["ve"].device
         cfg, h, d = self.cfg, self.cfg["hidden_size"], self.vis["d"]
-        B, L, Nv, R, S_all, nt = ctx["B"], ctx["L"], ctx["Nv"], ctx["R"], ctx["S_all"], ctx["nt"]
+        vtc_only = bool(ctx.get("vtc_only"))
+        B, L, Nv, nt = ctx["B"], ctx["L"], ctx["Nv"], ctx["nt"]
+        R, S_all = (0, 0) if vtc_only else (ctx["R"], ctx["S_all"])
         G = GradStore(named_params, dev, bert_grad_groups("text_encoder.", cfg))
         comm = self.comm
-        dfo = torch.zeros(S_all * R, h, dtype=torch.float32, device=dev)     # grad of the fusion output (scaled)
+        dfo = None if vtc_only else torch.zeros(S_all * R, h, dtype=torch.float32, device=dev)   # d fusion output (scaled)
 
         # ---- heads on top of the fusion encoder
         if ctx["use_mpm"] and g.get("mpm_loss") is not None:
@@ -945,17 +1000,18 @@ class AlproEngine:
             ops.masked_mean_bwd(dpool, m["pm"], B, m["Np"], h, dfo, R * h, L + 1)
         if ctx["use_mlm"] and g.get("mlm_loss") is not None:
             self._mlm_backward(P, ctx, G, g["mlm_loss"], dfo)
-        if g.get("itm_loss") is not None:
+        if not vtc_only and g.get("itm_loss") is not None:
             dlog = _empty((3 * B, 2), torch.float32, dev)
             ops.softmax_ce_bwd(ctx["itm_scores"], 2, ctx["ce_itm"], g["itm_loss"], S, hard=ctx["itm_labels"], out32=dlog)
             ops.small_linear_bwd(dlog, 2, None, ctx["fo"], R * h, P["itm_head.weight"].detach(), dfo, R * h, 1,
                                  G["itm_head.weight"], G["itm_head.bias"], 0, 3 * B, 2, h, dw_scale=inv)
 
         # ---- fusion encoder and the gather that built its input
-        dfi = self.bert.backward(P, self.W, ctx["fctx"], dfo, G, S)
         dte = torch.zeros(nt, L, h, dtype=torch.float32, device=dev)
         dve = torch.zeros(B, Nv, d, dtype=torch.float32, device=dev)
-        ops.fusion_gather_bwd(dfi, ctx["ti"], ctx["vi"], dte, dve, S_all, L, Nv, h)
+        if not vtc_only:
+            dfi = self.bert.backward(P, self.W, ctx["fctx"], dfo, G, S)
+            ops.fusion_gather_bwd(dfi, ctx["ti"], ctx["vi"], dte, dve, S_all, L, Nv, h)
 
         # ---- VTC
         if g.get("itc_loss") is not None:
@@ -967,16 +1023,23 @@ class AlproEngine:
             ops.softmax_ce_bwd(ctx["sim_t2v"], Gn, ctx["ce_t"], g["itc_loss"], 0.5 * S, hard=ctx["vtc_labels"], out32=ds_t)
             dvf = _empty((B, 256), torch.float32, dev)
             dtf = _empty((B, 256), torch.float32, dev)
-            dgt = _empty((Gn, 256), torch.float32, dev)
-            dgv = _empty((Gn, 256), torch.float32, dev)
+            ldg = ctx["gv"].stride(0)
+            dgvt = _empty((Gn, 512), torch.float32, dev)        # d gathered (video | text), same layout as the exchange
+            dgv, dgt = dgvt[:, :256], dgvt[:, 256:]
             # sim_v2t = vf gt^T / temp : d vf = ds_v gt / temp ; d gt = ds_v^T vf / temp
             ops.small_linear_bwd(ds_v, Gn, None, ctx["vf"], 256, ctx["gt"], dvf, 256, 0, dgt, None, 0, B, Gn, 256,
-                                 alpha=1.0, alpha_dev=temp, alpha_mode=2)
+                                 alpha=1.0, alpha_dev=temp, alpha_mode=2, ldw=ldg, lddw=512)
             ops.small_linear_bwd(ds_t, Gn, None, ctx["tf"], 256, ctx["gv"], dtf, 256, 0, dgv, None, 0, B, Gn, 256,
-                                 alpha=1.0, alpha_dev=temp, alpha_mode=2)
-            # backward of the all-gather: sum over ranks, keep the local slice (Horovod allgather grad semantics)
-            dvf.add_(comm.reduce_scatter_sum(dgv))
-            dtf.add_(comm.reduce_scatter_sum(dgt))
+                                 alpha=1.0, alpha_dev=temp, alpha_mode=2, ldw=ldg, lddw=512)
+            # backward of the all-gather: sum over ranks, keep the local slice (Horovod allgather grad semantics);
+            # one reduce-scatter for both feature sets
+            if comm.world > 1:
+                loc = comm.reduce_scatter_sum(dgvt)
+                dvf.add_(loc[:, :256])
+                dtf.add_(loc[:, 256:])
+            else:
+                dvf.add_(dgv)
+                dtf.add_(dgt)
             ops.temp_grad(ds_v, ctx["sim_v2t"], ds_t, ctx["sim_t2v"], temp, G["temp"].view(1), inv)
             for feat, nrm, dfeat, wname, x, ldx, dx in ((ctx["vf"], ctx["vnorm"], dvf, "vision_proj", ctx["ve"], Nv * d, dve),
                                                         (ctx["tf"], ctx["tnorm"], dtf, "text_proj", ctx["te"], L * h, dte)):

@@ -9,11 +9,64 @@ Same constructor arguments, batch keys, output dict keys, state_dict names/shape
 keys of config_release/base_model.json. Compute runs on the CUDA kernels through AlproEngine; there is no CPU path:
 calling forward on a CPU module raises.
 """
+import logging
+import weakref
+
 import torch
 from torch import nn
 
 from . import synth
 from .engine import AlproEngine
+
+LOGGER = logging.getLogger("alpro_b200")
+_LIVE = weakref.WeakSet()
+
+
+def live_models():
+    """Every AlproBaseModel instance alive in this process (the horovod stand-in's DistributedOptimizer uses it to
+    route gradient averaging through the model's flat gradient store)."""
+    return list(_LIVE)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# checkpoint helpers (reference: src/modeling/timesformer/helpers.py:26-56, 315-375; src/utils/load_save.py:73-140)
+# ---------------------------------------------------------------------------------------------------------------------
+def _nearest_index(n_out, n_in):
+    """Source index of F.interpolate(mode='nearest'): floor(dst * n_in / n_out)."""
+    return (torch.arange(n_out, dtype=torch.float32) * (n_in / n_out)).floor().long().clamp_(max=n_in - 1)
+
+
+def resize_spatial_embedding(pos_embed, num_patches):
+    """helpers.py:355-367: the cls slot is kept, the patch slots are nearest-resized as ONE flattened sequence."""
+    pos_embed = pos_embed.detach()
+    idx = _nearest_index(num_patches, pos_embed.shape[1] - 1) + 1
+    return torch.cat([pos_embed[:, :1], pos_embed[:, idx]], dim=1)
+
+
+def resize_temporal_embedding(time_embed, num_frames):
+    """helpers.py:370-375."""
+    time_embed = time_embed.detach()
+    return time_embed[:, _nearest_index(num_frames, time_embed.shape[1])]
+
+
+def read_timesformer_checkpoint(path):
+    """helpers.load_state_dict (helpers.py:26-56): accepts {'state_dict': ...} ('module.' prefix stripped),
+    {'model_state': ...} ('model.' prefix stripped) or a bare state dict."""
+    ckpt = torch.load(path, map_location="cpu")
+    if isinstance(ckpt, dict) and "state_dict" in ckpt:
+        return {(k[7:] if k.startswith("module") else k): v for k, v in ckpt["state_dict"].items()}
+    if isinstance(ckpt, dict) and "model_state" in ckpt:
+        return {(k[6:] if k.startswith("model") else k): v for k, v in ckpt["model_state"].items()}
+    return dict(ckpt)
+
+
+def _report_keys(what, loaded, own):
+    missing = sorted(k for k in own if k not in loaded)
+    unexpected = sorted(k for k in loaded if k not in own)
+    if missing or unexpected:
+        LOGGER.warning("%s: %d keys of the model not in the checkpoint %s; %d checkpoint keys not in the model %s", what,
+                       len(missing), missing[:8], len(unexpected), unexpected[:8])
+    return missing, unexpected
 
 
 def _cfg_dict(config):
@@ -57,7 +110,20 @@ def _default_dtype():
 
 
 class _Holder(nn.Module):
-    """Plain container used to reproduce the reference's module tree (and therefore its state_dict keys)."""
+    """Plain container used to reproduce the reference's module tree (and therefore its state_dict keys). Containers
+    with numeric children (`blocks`, `encoder.layer`, `mpm_head`) index like the reference's ModuleList / Sequential."""
+
+    def __getitem__(self, i):
+        try:
+            return self._modules[str(int(i))]
+        except (KeyError, ValueError, TypeError):
+            raise IndexError(i)
+
+    def __len__(self):
+        return sum(1 for k in self._modules if k.isdigit())
+
+    def __iter__(self):
+        return iter(self._modules[k] for k in sorted((k for k in self._modules if k.isdigit()), key=int))
 
 
 def _build_tree(root, spec, buffers=()):
@@ -159,6 +225,7 @@ class AlproBaseModel(nn.Module):
         self.engine = AlproEngine(self.kind, self._cfg, self._vis, dtype=_default_dtype(),
                                   num_entities=self._cfg.get("num_entities"))
         self._last_out = None
+        _LIVE.add(self)
 
     def set_compute_dtype(self, dtype, loss_scale=4096.0):
         """GEMM operand / saved-activation format: torch.float16 (default; backward carries a static loss scale) or
@@ -257,8 +324,20 @@ class AlproBaseModel(nn.Module):
             raise RuntimeError("alpro_b200 runs on CUDA only (sm_100a kernels); move the model and batch to a B200 "
                                "device — there is no CPU fallback.")
 
+    def _auto_attach(self):
+        """Under an initialised multi-rank process group (torchrun, or hvd.init() of the horovod stand-in) the VTC
+        feature exchange and the overlapped gradient averaging attach by themselves, as the reference model picks up
+        Horovod implicitly (alpro_models.py:110-111)."""
+        import torch.distributed as dist
+        from .engine import LocalComm
+        if isinstance(self.engine.comm, LocalComm) and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size() > 1:
+            from . import comm
+            comm.attach(self)
+
     def _run(self, batch):
         self._check_device(batch)
+        self._auto_attach()
         c = self._param_cache()
         names, params = c["names"], c["params"]
         need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
@@ -270,15 +349,45 @@ class AlproBaseModel(nn.Module):
             out[k] = v
         return out
 
+    def load_visual_weights(self, path):
+        """TimeSformer.load_state_dict(path) -> load_pretrained_kinetics (vit.py:514-533, helpers.py:315-352): keys
+        relative to `visual_encoder.model`, the 400-way classifier of the checkpoint is ignored, pos/time embeddings
+        are nearest-resized AT LOAD TIME to this model's grid / frame count; strict."""
+        sd = read_timesformer_checkpoint(path)
+        vm = self.visual_encoder.model
+        own = vm.state_dict()
+        sd["head.weight"], sd["head.bias"] = own["head.weight"], own["head.bias"]
+        n_patches = own["pos_embed"].shape[1] - 1
+        if "pos_embed" in sd and sd["pos_embed"].shape[1] != n_patches + 1:
+            sd["pos_embed"] = resize_spatial_embedding(sd["pos_embed"], n_patches)
+        if "time_embed" in sd and sd["time_embed"].shape[1] != own["time_embed"].shape[1]:
+            sd["time_embed"] = resize_temporal_embedding(sd["time_embed"], own["time_embed"].shape[1])
+        missing, unexpected = _report_keys("visual weights", sd, own)
+        bad = [k for k in own if k in sd and tuple(sd[k].shape) != tuple(own[k].shape)]
+        if missing or unexpected or bad:
+            # the reference logs 'Error in loading Kinetics pre-trained weights' and carries on with random weights
+            # (helpers.py:347-352); a silent random encoder is never what the caller wants, so this raises
+            raise RuntimeError(f"visual checkpoint {path!r} does not match the TimeSformer: missing {missing[:5]}, "
+                               f"unexpected {unexpected[:5]}, shape mismatch {bad[:5]}")
+        vm.load_state_dict(sd, strict=True)
+
     def load_separate_ckpt(self, visual_weights_path=None, bert_weights_path=None):
-        """alpro_models.py:45-51: loads TimeSformer weights. Accepts a state_dict file whose keys are relative to
-        visual_encoder.model (pos/time embeddings are resized at run time)."""
+        """alpro_models.py:45-51 (bert_weights_path is ignored there too: BERT comes from from_pretrained)."""
         if visual_weights_path:
-            sd = torch.load(visual_weights_path, map_location="cpu")
-            sd = sd.get("model_state", sd)
-            own = self.visual_encoder.model.state_dict()
-            self.visual_encoder.model.load_state_dict({k: v for k, v in sd.items() if k in own and v.shape == own[k].shape},
-                                                      strict=False)
+            self.load_visual_weights(visual_weights_path)
+
+    # ---- feature-level entry points of the reference classes
+    def _forward_visual_embeds(self, visual_inputs):
+        """alpro_models.py:186-194: [B,T,3,H,W] -> video_embeds [B, 1+N, d] (no gradient: the hand-written backward is
+        reached through forward(batch) only)."""
+        self._check_device({"visual_inputs": visual_inputs})
+        with torch.no_grad():
+            return self.engine.visual_features(self._tensor_dict(), visual_inputs)
+
+    def _forward_text_feats(self, batch):
+        """alpro_models.py:196-207: text_embeds [B,L,h], normalised text_feat [B,256] (no gradient)."""
+        with torch.no_grad():
+            return self.engine.text_features(self._tensor_dict(), batch["text_input_ids"], batch["text_input_mask"])
 
 
 def _public(out, keys):
@@ -304,23 +413,98 @@ class AlproForVideoTextRetrieval(AlproBaseModel):
 
 
 class Prompter(AlproBaseModel):
+    """Teacher that turns a clip into soft entity labels (alpro_models.py:389-630)."""
     kind = "prompter"
 
     def __init__(self, config, video_enc_cfg, input_format="RGB"):
         super().__init__(config, input_format=input_format, video_enc_cfg=video_enc_cfg)
         self.entity_num = self._cfg["num_entities"]
         self.prompt_initialized = False
-        self.ignore_threshold = 0.2
+        self.ignore_threshold = 0.2         # compared with the argmax INDEX in the reference (:527), kept as is
+
+    def load_pretrained_weights_without_prompts(self, ckpt_path):
+        """alpro_models.py:404-428: everything but the *_prompt_feat buffers, non-strict, differences logged."""
+        LOGGER.info("Loading weights for teacher model.")
+        loaded = torch.load(ckpt_path, map_location="cpu")
+        _report_keys("teacher weights", loaded, self.state_dict())
+        self.load_state_dict({k: v for k, v in loaded.items() if "prompt_feat" not in k}, strict=False)
+
+    def build_text_prompts(self, prompts):
+        """alpro_models.py:430-507: encode every prompt (chunks of 10 000) with the text encoder, project + normalise the
+        [CLS] output, average over the templates of each entity -> video_prompt_feat / image_prompt_feat [E,256]."""
+        assert not self.prompt_initialized, "Repetitively building prompts?"
+        if self.training:
+            self.eval()
+        P = self._tensor_dict()
+        dev = self.temp.device
+        if not self.temp.is_cuda:
+            raise RuntimeError("alpro_b200 runs on CUDA only (sm_100a kernels): move the model to the device first")
+        with torch.no_grad():
+            for key, buf in (("batch_enc_video_prompts", "video_prompt_feat"),
+                             ("batch_enc_image_prompts", "image_prompt_feat")):
+                ids_all, mask_all = prompts[key].input_ids, prompts[key].attention_mask
+                feats = []
+                for s0 in range(0, ids_all.shape[0], 10000):
+                    ids = ids_all[s0:s0 + 10000].to(dev)
+                    mask = mask_all[s0:s0 + 10000].to(dev)
+                    _, f = self.engine.text_features(P, ids, mask)
+                    feats.append(f)
+                f = torch.cat(feats, dim=0)
+                n_templates = int(f.shape[0] / self.entity_num)
+                f = torch.stack(f.chunk(n_templates), dim=1).mean(dim=1)
+                getattr(self, buf).copy_(f)       # in place: keeps the registered buffer (and the parent's tensor map)
+        self.prompt_initialized = True
+
+    def _forward_visual_embeds(self, visual_inputs):
+        """alpro_models.py:509-523: (video_embeds, normalised video_feat)."""
+        self._check_device({"visual_inputs": visual_inputs})
+        with torch.no_grad():
+            return self.engine.visual_feat(self._tensor_dict(), visual_inputs)
+
+    def get_pseudo_labels(self, batch):
+        """alpro_models.py:531-551: (soft labels [B,E], ignore mask bool [B]); always eval + no_grad."""
+        if self.training:
+            self.eval()
+        self._check_device({"visual_inputs": batch["crop_visual_inputs"]})
+        with torch.no_grad():
+            return self.engine.pseudo_labels(self._tensor_dict(), batch["crop_visual_inputs"], batch.get("type", "video"))
+
+    def forward_feats(self, batch):
+        """alpro_models.py:597-630 (no gradient; training the teacher goes through forward(batch))."""
+        self._check_device(batch)
+        with torch.no_grad():
+            P = self._tensor_dict()
+            self.engine.clamp_temp(P)
+            ve, vf = self.engine.visual_feat(P, batch["visual_inputs"])
+            te, tf = self.engine.text_features(P, batch["text_input_ids"], batch["text_input_mask"])
+        return ve, vf, te, tf
+
+    def forward(self, batch):
+        """alpro_models.py:553-595: the video-text contrastive step that trains the teacher
+        (run_pretrain_contrastive_only.py): itc_loss (autograd-connected), itc_labels, i2t_scores, t2i_scores."""
+        out = self._run(batch)
+        return _public(out, ("itc_loss", "itc_labels", "i2t_scores", "t2i_scores"))
 
 
 class AlproForPretrain(AlproBaseModel):
     kind = "pretrain"
 
     def __init__(self, config, video_enc_cfg, input_format="RGB"):
+        self._ctor = (config, video_enc_cfg, input_format)
         super().__init__(config, input_format=input_format, video_enc_cfg=video_enc_cfg)
         self.use_mask_prob = 0
         for p in self.prompter.parameters():      # teacher is frozen (eval + no_grad in the reference, :532-535)
             p.requires_grad_(False)
+
+    def _spec(self):
+        # the `prompter.` subtree is a real Prompter module (same state_dict keys)
+        full = synth.model_spec(self.kind, self._cfg, self._vis, self._cfg.get("num_entities"))
+        return type(full)((k, v) for k, v in full.items() if not k.startswith("prompter."))
+
+    def _make(self, temp):
+        config, video_enc_cfg, input_format = self._ctor
+        super()._make(temp)
+        self.prompter = Prompter(config, video_enc_cfg, input_format)      # alpro_models.py:63
 
     def forward(self, batch):
         out = self._run(batch)
@@ -330,26 +514,16 @@ class AlproForPretrain(AlproBaseModel):
         return res
 
     def build_text_prompts(self, prompts):
-        """Prompter.build_text_prompts (alpro_models.py:430-507): encode every prompt with the teacher's text encoder,
-        normalise, average over templates -> prompter.{video,image}_prompt_feat."""
-        from .engine import BertEncoder, _PrefixedCache
-        P = {k[len("prompter."):]: v for k, v in self._tensor_dict().items() if k.startswith("prompter.")}
-        eng = self.engine
-        bert = BertEncoder("text_encoder.", eng.cfg, eng.dtype)
-        cache = _PrefixedCache(eng.W, "prompter.")
-        E = self._cfg["num_entities"]
-        with torch.no_grad():
-            for key, buf in (("batch_enc_video_prompts", "video_prompt_feat"), ("batch_enc_image_prompts", "image_prompt_feat")):
-                ids = prompts[key].input_ids.cuda()
-                mask = prompts[key].attention_mask.cuda().contiguous()
-                feats = []
-                for s in range(0, ids.shape[0], 10000):
-                    i, m = ids[s:s + 10000].contiguous(), mask[s:s + 10000].contiguous()
-                    x32, x16, _ = bert.embed(P, i, False)
-                    te, _, _ = bert.forward(P, cache, x32, x16, eng._text_mask_add(m), i.shape[0], i.shape[1], "text", False)
-                    f, _ = eng._proj_norm(P, te, i.shape[1] * eng.cfg["hidden_size"], "text_proj", i.shape[0])
-                    feats.append(f)
-                f = torch.cat(feats, dim=0)
-                f = torch.stack(f.chunk(f.shape[0] // E), dim=1).mean(dim=1)
-                getattr(self.prompter, buf).copy_(f)
-        self.prompter.prompt_initialized = True
+        """alpro_models.py:73-74."""
+        self.prompter.build_text_prompts(prompts)
+
+    def get_pseudo_labels(self, batch):
+        """alpro_models.py:76-77."""
+        return self.prompter.get_pseudo_labels(batch)
+
+    def load_separate_ckpt(self, visual_weights_path=None, bert_weights_path=None, prompter_weights_path=None):
+        """alpro_models.py:375-387."""
+        if visual_weights_path:
+            self.load_visual_weights(visual_weights_path)
+        if prompter_weights_path is not None:
+            self.prompter.load_pretrained_weights_without_prompts(prompter_weights_path)

@@ -107,7 +107,11 @@ def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, a
                                     ctypes.byref(ep), _stream()), "alpro_gemm16")
     if prof is not None:
         e1.record()
-        prof.append((M, N, K, e0, e1))
+        # algorithmic bytes of this launch: both 16-bit operands once + every epilogue stream at its real width
+        nbytes = 2.0 * (M * K + N * K) + M * N * (4.0 * (out32 is not None) + 2.0 * (out16 is not None)
+                                                   + 2.0 * (out16b is not None) + 4.0 * (resid is not None)
+                                                   + 2.0 * (aux is not None))
+        prof.append((M, N, K, e0, e1, nbytes))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -369,3 +369,39 @@ def pretrain_forward(sd, cfg, vis, batch, rank=0, gather=None, sampler=argmax_sa
         out["mpm_labels"] = soft
         out["_mpm_ignore"] = ignore
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Prompter (teacher)                             src/modeling/alpro_models.py:389-630
+# --------------------------------------------------------------------------------------------------------------
+def prompter_forward(sd, cfg, vis, batch, rank=0, gather=None):
+    """Prompter.forward alpro_models.py:553-595 (+ forward_feats :597-630): the contrastive objective alone, with the
+    reference's soft-target formulation -sum(log_softmax(sim) * targets).mean(); returns its four outputs.
+    `sd` holds the Prompter's own state dict (no 'prompter.' prefix)."""
+    temp = sd["temp"].clamp(0.001, 0.5)
+    video_embeds = visual_forward(sd, "visual_encoder.model.", batch["visual_inputs"], vis)
+    text_embeds = bert_text(sd, "text_encoder.", batch["text_input_ids"], batch["text_input_mask"], cfg)
+    vf = F.normalize(F.linear(video_embeds[:, 0], sd["vision_proj.weight"], sd["vision_proj.bias"]), dim=-1)
+    tf = F.normalize(F.linear(text_embeds[:, 0], sd["text_proj.weight"], sd["text_proj.bias"]), dim=-1)
+    gv = gather(vf) if gather else vf
+    gt = gather(tf) if gather else tf
+    sim_v2t = vf @ gt.t() / temp
+    sim_t2v = tf @ gv.t() / temp
+    b = vf.shape[0]
+    targets = torch.zeros_like(sim_v2t)
+    targets[:, b * rank:b * (rank + 1)] = torch.eye(b, device=vf.device)
+    lv, lt = F.log_softmax(sim_v2t, dim=1), F.log_softmax(sim_t2v, dim=1)
+    loss = 0.5 * (-(lv * targets).sum(dim=1).mean() - (lt * targets).sum(dim=1).mean())
+    return dict(itc_loss=loss, itc_labels=targets.max(dim=1)[1], i2t_scores=lv, t2i_scores=lt,
+                _video_embeds=video_embeds, _video_feat=vf, _text_embeds=text_embeds, _text_feat=tf)
+
+
+def build_text_prompts(sd, cfg, ids, mask, num_entities):
+    """Prompter.build_text_prompts alpro_models.py:430-507 for one prompt set: text-encode every prompt, project and
+    normalise the [CLS] output, then average over templates — prompts are laid out template-major
+    (chunk(num_templates) then stack(dim=1), :470-474)."""
+    with torch.no_grad():
+        te = bert_text(sd, "text_encoder.", ids, mask, cfg)
+        feat = F.normalize(F.linear(te[:, 0], sd["text_proj.weight"], sd["text_proj.bias"]), dim=-1)
+        n_templates = int(feat.shape[0] / num_entities)
+        return torch.stack(feat.chunk(n_templates), dim=1).mean(dim=1)

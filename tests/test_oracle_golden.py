@@ -91,3 +91,71 @@ def test_state_dict_schema_matches_reference():
         spec = synth.model_spec(kind, cfg["bert"], cfg["vis"], cfg["num_entities"])
         ref = {k: tuple(v.shape) for k, v in model.state_dict().items()}
         assert ref == {k: tuple(v) for k, v in spec.items()}
+
+
+@pytest.mark.reference
+def test_prompter_oracle_matches_live_reference():
+    """Pins oracle.prompter_forward / pseudo_labels / build_text_prompts against the unmodified reference Prompter
+    (alpro_models.py:389-630) on the tiny config: Prompter.forward outputs + gradients, get_pseudo_labels, and
+    build_text_prompts (whose `.cuda()` calls are neutralised for the CPU run)."""
+    from types import SimpleNamespace
+    from alpro_b200 import synth
+    from oracle import ref_harness
+    cfg = configs.tiny("prompter", B=3, T=2, img=64, L=8, seed=17)
+    model = ref_harness.build_reference_model("prompter", cfg["bert"], cfg["video"],
+                                              vis_dims=(cfg["vis"]["d"], cfg["vis"]["depth"], cfg["vis"]["heads"]),
+                                              num_entities=cfg["num_entities"])
+    spec = synth.model_spec("prompter", cfg["bert"], cfg["vis"], cfg["num_entities"])
+    sd = synth.synth_state_dict(spec, cfg["seed"])
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    batch = synth.synth_batch("pretrain", cfg["B"], cfg["T"], cfg["img"], cfg["L"], cfg["bert"]["vocab_size"],
+                              seed=cfg["seed"], num_entities=cfg["num_entities"])
+    # ---- forward (contrastive objective) + gradients
+    ref = model(batch)
+    ref["itc_loss"].backward()
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    for k in list(sd_o):
+        c = synth.canonical_name(k)
+        if c != k:
+            sd_o[k] = sd_o[c]
+    for v in sd_o.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    out = alpro_oracle.prompter_forward(sd_o, cfg["bert"], cfg["vis"], batch)
+    out["itc_loss"].backward()
+    for k in ("itc_loss", "i2t_scores", "t2i_scores"):
+        assert helpers.rel_err(out[k].detach(), ref[k].detach()) < TOL, k
+    assert out["itc_labels"].tolist() == ref["itc_labels"].tolist()
+    checked = 0
+    for n, p in model.named_parameters():
+        if p.grad is None or float(p.grad.abs().max()) < 1e-9:
+            continue
+        assert helpers.rel_err(sd_o[n].grad, p.grad) < 1e-4, n
+        checked += 1
+    assert checked > 40
+    # ---- pseudo labels
+    soft_r, ign_r = model.get_pseudo_labels(batch)
+    sd_p = {"prompter." + k: v for k, v in sd.items()}
+    soft_o, ign_o = alpro_oracle.pseudo_labels(sd_p, cfg["bert"], cfg["vis"], batch)
+    assert helpers.rel_err(soft_o, soft_r) < TOL and ign_o.tolist() == ign_r.tolist()
+    # ---- prompts: E entities x 3 templates, template-major
+    E, nt, Lp = cfg["num_entities"], 3, 6
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(4, cfg["bert"]["vocab_size"], (E * nt, Lp), generator=g)
+    ids[:, 0] = 1
+    mask = torch.ones(E * nt, Lp, dtype=torch.long)
+    mask[::2, -2:] = 0
+
+    class _T(torch.Tensor):
+        def cuda(self, *a, **k):     # alpro_models.py:455-456 moves the chunk to the GPU; there is none here
+            return self.as_subclass(torch.Tensor)
+
+        def __getitem__(self, i):
+            return torch.Tensor.__getitem__(self, i).as_subclass(_T)
+    enc = SimpleNamespace(input_ids=ids.as_subclass(_T), attention_mask=mask.as_subclass(_T))
+    model.prompt_initialized = False
+    model.build_text_prompts({"batch_enc_video_prompts": enc, "batch_enc_image_prompts": enc})
+    want = alpro_oracle.build_text_prompts(sd, cfg["bert"], ids, mask, E)
+    assert helpers.rel_err(want, model.video_prompt_feat) < TOL
+    assert helpers.rel_err(want, model.image_prompt_feat) < TOL
