@@ -83,7 +83,8 @@ for _name, (_res, _args) in PROTOS.items():
     _fn.argtypes = _args
     globals()[_name] = _fn
 
-_NO_LAUNCH = {"alpro_last_error", "alpro_version", "alpro_num_sms"}
+_NO_LAUNCH = {"alpro_last_error", "alpro_version", "alpro_num_sms", "alpro_comm_unique_id", "alpro_comm_init",
+              "alpro_comm_destroy", "alpro_comm_rank", "alpro_comm_world"}
 
 
 class _Counting:

@@ -68,7 +68,7 @@ def build(force=False, verbose=False):
                 if rc != 0:
                     raise RuntimeError(f"nvcc failed on {s}")
     if jobs or force or _stale(LIB_PATH, objs):
-        cmd = [NVCC, "-shared", "-o", LIB_PATH] + objs + ["-Xcompiler", "-fPIC",
+        cmd = [NVCC, "-shared", "-o", LIB_PATH] + objs + ["-Xcompiler", "-fPIC", "-ldl",
                                                           "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

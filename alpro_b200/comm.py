@@ -36,6 +36,63 @@ class TorchDistComm:
         return out
 
 
+class NcclAbiComm:
+    """The same exchange through the library's own C-ABI communicator (alpro_comm_*, include/alpro_b200.h) instead of
+    torch.distributed — what a non-Python host binds. `id128` comes from NcclAbiComm.unique_id() on rank 0, shipped to
+    the other ranks out of band (file, socket, torch.distributed.broadcast_object_list ...)."""
+
+    def __init__(self, world, rank, id128):
+        import ctypes
+        from . import _lib
+        self._lib, self._ct = _lib, ctypes
+        self.world, self.rank = world, rank
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(id128))
+        _lib.check(_lib.lib.alpro_comm_init(ctypes.byref(h), world, rank, ctypes.cast(buf, ctypes.c_void_p)),
+                   "alpro_comm_init")
+        self._h = h
+
+    @staticmethod
+    def unique_id():
+        import ctypes
+        from . import _lib
+        buf = (ctypes.c_char * 128)()
+        _lib.check(_lib.lib.alpro_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)), "alpro_comm_unique_id")
+        return bytes(buf)
+
+    _KIND = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def all_gather(self, x):
+        x = x.contiguous()
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        self._lib.check(self._lib.counted.alpro_comm_allgather(self._h, x.data_ptr(), out.data_ptr(), x.numel(),
+                                                               self._KIND[x.dtype], self._stream()), "alpro_comm_allgather")
+        return out
+
+    def reduce_scatter_sum(self, g):
+        g = g.contiguous()
+        b = g.shape[0] // self.world
+        out = torch.empty((b,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        self._lib.check(self._lib.counted.alpro_comm_reduce_scatter(self._h, g.data_ptr(), out.data_ptr(), out.numel(),
+                                                                    self._KIND[g.dtype], self._stream()),
+                        "alpro_comm_reduce_scatter")
+        return out
+
+    def all_reduce_(self, t, average=True):
+        assert t.is_contiguous()
+        self._lib.check(self._lib.counted.alpro_comm_allreduce(self._h, t.data_ptr(), t.numel(), self._KIND[t.dtype],
+                                                               int(average), self._stream()), "alpro_comm_allreduce")
+        return t
+
+    def close(self):
+        if self._h:
+            self._lib.lib.alpro_comm_destroy(self._h)
+            self._h = None
+
+
 class BucketedAllReduce:
     """Gradient averaging overlapped with the backward pass.
 

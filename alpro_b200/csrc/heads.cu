@@ -4,6 +4,7 @@
 // operands (SURVEY.md §7 "Precision vs the 1e-3 gate").
 #include "common.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace alpro {
 namespace {
@@ -301,6 +302,57 @@ __global__ void neg_weights_kernel(const float* __restrict__ sim, long long ld, 
   for (int c = lane; c < b; c += 32) w[r * b + c] = c == r ? 0.f : __expf(sim[r * ld + col0 + c] - mx) / s;
 }
 
+// Hard-negative DRAW fused with the weights (alpro_models.py:301-316, 833-844: `torch.multinomial(weights[b], 1).item()`
+// per row, 2*B host synchronisations per step in the reference): one warp per row computes the softmax weights of the
+// local block with the diagonal excluded and samples one index by inverse CDF with a Philox4x32-10 uniform
+// (counter = (row, draw, 0, 0), key = seed). The index is a device int64; nothing returns to the host.
+__global__ void neg_sample_kernel(const float* __restrict__ sim, long long ld, int col0, int b, uint32_t seed_lo,
+                                  uint32_t seed_hi, uint32_t draw, float* __restrict__ w, long long* __restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= b) return;
+  const float* x = sim + r * ld + col0;
+  float mx = -INFINITY;
+  for (int c = lane; c < b; c += 32)
+    if (c != r) mx = fmaxf(mx, x[c]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int c = lane; c < b; c += 32)
+    if (c != r) s += __expf(x[c] - mx);
+  s = warp_sum(s);
+  if (w)
+    for (int c = lane; c < b; c += 32) w[r * b + c] = c == r ? 0.f : __expf(x[c] - mx) / s;
+  const Philox4 rnd = philox4x32_10(static_cast<uint32_t>(r), draw, 0u, 0u, seed_lo, seed_hi);
+  const float u = (static_cast<float>(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // 24-bit uniform in (0, 1)
+  const float target = u * s;
+  float run = 0.f;
+  int pick = -1, last = -1;
+  for (int c0 = 0; c0 < b && pick < 0; c0 += 32) {
+    const int c = c0 + lane;
+    const float e = (c < b && c != r) ? __expf(x[c] - mx) : 0.f;
+    float sc = e;   // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) sc += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, e > 0.f && run + sc > target);
+    const unsigned any = __ballot_sync(0xffffffffu, e > 0.f);
+    if (any) last = c0 + 31 - __clz(any);
+    if (hit) pick = c0 + __ffs(hit) - 1;
+    run += __shfl_sync(0xffffffffu, sc, 31);
+  }
+  if (pick < 0) pick = last >= 0 ? last : (r == 0 && b > 1 ? 1 : 0);   // rounding at the top of the CDF
+  if (lane == 0) idx[r] = pick;
+}
+
+__global__ void philox_kat_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Philox4 v = philox4x32_10(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5]);
+  out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+}
+
 // out16 = dy * dact, dact = gelu'(pre) saved by the forward GEMM epilogue   (MLM transform backward, xbert.py:659-661)
 __global__ void gelu_grad_mul_kernel(const float* __restrict__ dy, const uint16_t* __restrict__ pre, int pre_fmt,
                                      uint16_t* __restrict__ out, int out_fmt, long long n) {
@@ -493,6 +545,22 @@ extern "C" int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, 
   ALPRO_REQUIRE(sim && w && b > 0, "alpro_neg_weights: bad args");
   neg_weights_kernel<<<static_cast<unsigned>(cdiv(b, 4)), 128, 0, ST>>>(sim, ld, col0, b, w);
   ALPRO_CHECK_LAUNCH("alpro_neg_weights");
+  return 0;
+}
+
+extern "C" int alpro_neg_sample(const float* sim, int64_t ld, int col0, int b, uint32_t seed_lo, uint32_t seed_hi,
+                                uint32_t draw, float* w, int64_t* idx, void* stream) {
+  ALPRO_REQUIRE(sim && idx && b > 0, "alpro_neg_sample: bad args");
+  neg_sample_kernel<<<static_cast<unsigned>(cdiv(b, 4)), 128, 0, ST>>>(sim, ld, col0, b, seed_lo, seed_hi, draw, w,
+                                                                      reinterpret_cast<long long*>(idx));
+  ALPRO_CHECK_LAUNCH("alpro_neg_sample");
+  return 0;
+}
+
+extern "C" int alpro_philox4x32_10(const uint32_t* ctr_key, uint32_t* out, int n, void* stream) {
+  ALPRO_REQUIRE(ctr_key && out && n > 0, "alpro_philox4x32_10: bad args");
+  philox_kat_kernel<<<static_cast<unsigned>(cdiv(n, 128)), 128, 0, ST>>>(ctr_key, out, n);
+  ALPRO_CHECK_LAUNCH("alpro_philox4x32_10");
   return 0;
 }
 

@@ -690,8 +690,8 @@ class LocalComm:
 
 
 def multinomial_sampler(weights):
-    """Row-wise multinomial draw on the device (torch.multinomial(w[b], 1) per row in the reference,
-    alpro_models.py:301-316, without the 2*B host synchronisations)."""
+    """Row-wise multinomial draw through torch (torch.multinomial(w[b], 1) per row in the reference,
+    alpro_models.py:301-316). Kept as an alternative `engine.sampler`; the default is the fused Philox kernel."""
     return torch.multinomial(weights, 1).squeeze(1)
 
 
@@ -716,7 +716,9 @@ class AlproEngine:
         self.num_entities = num_entities
         if kind == "pretrain":
             self.t_visual = VisualEncoder("prompter.visual_encoder.model.", vis, dtype)
-        self.sampler = multinomial_sampler
+        self.sampler = None              # None: fused Philox draw; or a callable on the [B,B] weights (tests: argmax)
+        self.neg_seed = 0x5851F42D4C957F2D
+        self._draw = 0
         self.comm = LocalComm()
         self.last_grads = None
         self.base_seed = 0x5DEECE66
@@ -853,15 +855,23 @@ class AlproEngine:
             return out, ctx
 
         # ---- hard negatives (alpro_models.py:288-316)
-        w_t2v = _empty((B, B), torch.float32, dev)
-        w_v2t = _empty((B, B), torch.float32, dev)
-        ops.neg_weights(sim_t2v, B * comm.rank, B, w_t2v)
-        ops.neg_weights(sim_v2t, B * comm.rank, B, w_v2t)
-        if B > 1:
+        if B <= 1:
+            neg_video = neg_text = torch.zeros(1, dtype=torch.int64, device=dev)
+        elif self.sampler is None:
+            # production path: weights + the per-row multinomial draw in ONE kernel per direction (Philox4x32-10 keyed by
+            # (neg_seed, step); the reference draws row by row with 2*B .item() synchronisations)
+            self._draw += 2
+            neg_video = _empty((B,), torch.int64, dev)
+            neg_text = _empty((B,), torch.int64, dev)
+            ops.neg_sample(sim_t2v, B * comm.rank, B, self.neg_seed, self._draw, neg_video)      # a negative video per text
+            ops.neg_sample(sim_v2t, B * comm.rank, B, self.neg_seed, self._draw + 1, neg_text)   # a negative text per video
+        else:
+            w_t2v = _empty((B, B), torch.float32, dev)
+            w_v2t = _empty((B, B), torch.float32, dev)
+            ops.neg_weights(sim_t2v, B * comm.rank, B, w_t2v)
+            ops.neg_weights(sim_v2t, B * comm.rank, B, w_v2t)
             neg_video = self.sampler(w_t2v)    # a negative video for each text
             neg_text = self.sampler(w_v2t)     # a negative text for each video
-        else:
-            neg_video = neg_text = torch.zeros(1, dtype=torch.int64, device=dev)
 
         # ---- one batched fusion pass: positives | (text_i, video_neg_i) | (text_neg_i, video_i) | MLM pairs
         ar = torch.arange(B, device=dev, dtype=torch.int64)

@@ -111,7 +111,12 @@ def gemm16(a, b, *, a_layout=KMAJOR, b_layout=KMAJOR, bias=None, act=ACT_NONE, a
         nbytes = 2.0 * (M * K + N * K) + M * N * (4.0 * (out32 is not None) + 2.0 * (out16 is not None)
                                                    + 2.0 * (out16b is not None) + 4.0 * (resid is not None)
                                                    + 2.0 * (aux is not None))
-        prof.append((M, N, K, e0, e1, nbytes))
+        tag = ("A" + ("mn" if a_layout == MNMAJOR else "k") + " B" + ("mn" if b_layout == MNMAJOR else "k")
+               + (" splitK" if split_k else "") + (" act%d" % act if act else "") + (" resid" if resid is not None else "")
+               + (" o32" if out32 is not None else "") + (" o16" if out16 is not None else "")
+               + (" o16b" if out16b is not None else "") + (" aux" if aux is not None else "")
+               + (" rs" if row_scale is not None else ""))
+        prof.append((M, N, K, e0, e1, nbytes, tag))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -351,6 +356,15 @@ def take_rows_bwd(dout, R, s0, n, L, h, dsrc):
 
 def neg_weights(sim, col0, b, w):
     check(_L.alpro_neg_weights(_p(sim), sim.stride(0), col0, b, _p(w), _s()), "alpro_neg_weights")
+
+
+def neg_sample(sim, col0, b, seed, draw, idx, w=None):
+    check(_L.alpro_neg_sample(_p(sim), sim.stride(0), col0, b, seed & 0xffffffff, (seed >> 32) & 0xffffffff,
+                              draw & 0xffffffff, _p(w), _p(idx), _s()), "alpro_neg_sample")
+
+
+def philox4x32_10(ctr_key, out):
+    check(_L.alpro_philox4x32_10(_p(ctr_key), _p(out), ctr_key.shape[0], _s()), "alpro_philox4x32_10")
 
 
 def gelu_grad_mul(dy32, pre16, out16):

@@ -226,6 +226,13 @@ int alpro_gelu_grad_mul(const float* dy, const void* dact, int dact_fmt, void* o
 int alpro_pseudo_labels(const float* sim, int R, int C, float* soft, uint8_t* ignore, void* stream);
 /* hard-negative sampling weights: softmax of the local sim block with -inf diagonal (alpro_models.py:288-299) */
 int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, float* w, void* stream);
+/* the weights above AND the draw `torch.multinomial(weights[r], 1)` of every row r (alpro_models.py:301-316, 833-844) in
+ * one launch: idx[r] (int64, device) ~ Categorical(w[r, :]) by inverse CDF on a Philox4x32-10 uniform with
+ * counter (r, draw, 0, 0) and key (seed_lo, seed_hi). w may be null. No host synchronisation. */
+int alpro_neg_sample(const float* sim, int64_t ld, int col0, int b, uint32_t seed_lo, uint32_t seed_hi, uint32_t draw,
+                     float* w, int64_t* idx, void* stream);
+/* known-answer access to the generator: n x (4 counter words, 2 key words) -> n x 4 output words */
+int alpro_philox4x32_10(const uint32_t* ctr_key, uint32_t* out, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused optimizer step over flat buffers (alpro_b200/csrc/optim.cu)
@@ -244,6 +251,26 @@ int alpro_adamw_prepare(const float* gnorm_sq, float lr, float beta1, float beta
 /* alpro_adamw_step with the step size read from device memory (written by alpro_adamw_prepare) */
 int alpro_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
                          const float* step_size_dev, float lr_wd, const float* gnorm_sq, float max_norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Collectives of the data-parallel path over NCCL / NVLink (alpro_b200/csrc/comm.cu). One communicator per process and
+ * GPU (the caller's CURRENT device at alpro_comm_init). NCCL is bound at run time (dlopen libnccl.so.2);
+ * ALPRO_ENOTSUP when it cannot be loaded. dtype: 0 = f32, 1 = f16, 2 = bf16. All calls are stream-ordered.
+ * Replaces hvd.allgather (alpro_models.py:110-111, 764-765), its gradient (sum over ranks, local slice) and the
+ * gradient averaging of hvd.DistributedOptimizer (run_video_retrieval.py:320-323, 444).
+ */
+/* rank 0 creates the 128-byte id and ships it to the other ranks by any out-of-band means */
+int alpro_comm_unique_id(void* id128);
+int alpro_comm_init(void** comm_out, int world, int rank, const void* id128);
+int alpro_comm_destroy(void* comm);
+int alpro_comm_rank(void* comm);
+int alpro_comm_world(void* comm);
+/* recv[world * count_per_rank] = concatenation of every rank's send[count_per_rank] in rank order */
+int alpro_comm_allgather(void* comm, const void* send, void* recv, int64_t count_per_rank, int dtype, void* stream);
+/* recv[count_per_rank] = slice `rank` of the element-wise SUM over ranks of send[world * count_per_rank] */
+int alpro_comm_reduce_scatter(void* comm, const void* send, void* recv, int64_t count_per_rank, int dtype, void* stream);
+/* buf[count] = sum (average != 0: mean) over ranks, in place */
+int alpro_comm_allreduce(void* comm, void* buf, int64_t count, int dtype, int average, void* stream);
 
 #ifdef __cplusplus
 }

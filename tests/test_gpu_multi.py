@@ -49,3 +49,66 @@ def test_two_rank_step_matches_global_oracle():
     print("dp_parity", res)
     assert res["neg_indices_equal"] and res["grads_identical_across_ranks"]
     assert res["max_rel_loss"] < 1e-3 and res["max_rel_grad"] < 3e-2, res
+
+
+def _abi_worker(rank, world, idq, outq):
+    torch.cuda.set_device(rank)
+    from alpro_b200.comm import NcclAbiComm
+    if rank == 0:
+        uid = NcclAbiComm.unique_id()
+        for _ in range(world - 1):
+            idq.put(uid)
+    else:
+        uid = idq.get(timeout=120)
+    comm = NcclAbiComm(world, rank, uid)          # alpro_comm_init: no torch.distributed anywhere in this process
+    dev = torch.device("cuda", rank)
+    x = torch.full((3, 512), float(rank + 1), device=dev)
+    g = comm.all_gather(x)
+    ok = g.shape == (3 * world, 512) and all(float(g[3 * r, 0]) == r + 1 for r in range(world))
+    full = torch.arange(3 * world * 4, dtype=torch.float32, device=dev).view(3 * world, 4)
+    rs = comm.reduce_scatter_sum(full * (rank + 1))
+    want = full * sum(r + 1 for r in range(world))
+    ok = ok and torch.equal(rs, want[3 * rank:3 * rank + 3])
+    t = torch.arange(1000, dtype=torch.float32, device=dev) * (rank + 1)
+    comm.all_reduce_(t, average=True)
+    ok = ok and torch.allclose(t, torch.arange(1000, dtype=torch.float32, device=dev) * (sum(r + 1 for r in range(world)) / world))
+    h = torch.ones(64, device=dev, dtype=torch.bfloat16) * (rank + 1)
+    comm.all_reduce_(h, average=False)
+    ok = ok and float(h[0]) == sum(r + 1 for r in range(world))
+    # the engine's VTC exchange through the C-ABI communicator: a retrieval step of the tiny config
+    from oracle import configs
+    from tests import helpers
+    from tests.test_gpu_parity import build_cuda_model, to_cuda
+    from alpro_b200 import synth
+    cfg = dict(configs.GOLDEN["tiny_retrieval"])
+    spec, sd, _ = helpers.make_inputs(cfg)
+    batch = synth.synth_batch("retrieval", cfg["B"], cfg["T"], cfg["img"], cfg["L"], cfg["bert"]["vocab_size"], seed=100 + rank)
+    model = build_cuda_model(cfg, sd)
+    model.engine.comm = comm
+    out = model(to_cuda(batch))
+    (out["itc_loss"] + out["itm_loss"]).backward()
+    comm.all_reduce_(model.engine.last_grads.flat, average=True)
+    torch.cuda.synchronize()
+    outq.put((rank, bool(ok), float(out["itc_loss"]), float(out["itm_loss"]),
+              float(model.engine.last_grads.flat.double().norm())))
+    comm.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_c_abi_communicator_two_ranks():
+    """alpro_comm_* (include/alpro_b200.h): semantics of the three collectives, and the same data-parallel step as the
+    torch.distributed path (compared with dp_parity's oracle through the losses of the test above: same seeds)."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    idq, outq = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_abi_worker, args=(r, world, idq, outq)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict((r, rest) for r, *rest in (outq.get(timeout=600) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got[0][0] and got[1][0]
+    assert abs(got[0][3] - got[1][3]) <= 1e-6 * max(1.0, got[0][3])     # averaged gradients: same norm on both ranks
+    assert got[0][1] > 0 and got[1][1] > 0
