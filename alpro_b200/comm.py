@@ -175,6 +175,67 @@ class BucketedAllReduce:
         self._G = None
 
 
+class NvlGradReducer(BucketedAllReduce):
+    """Gradient averaging by OUR kernel over NVLink peer memory (csrc/allreduce.cu) instead of ncclAllReduce.
+
+    The engine's flat gradient store lives in symmetric memory (torch.distributed._symmetric_memory: cuMem allocation
+    mapped into every rank of the node, plus an NVSwitch multicast mapping when the fabric offers one). A ready bucket is
+    reduced on the side stream by   barrier -> alpro_nvl_allreduce -> barrier   where the barriers are the symmetric
+    memory's signal-pad barriers (one tiny kernel each) and the reduction is a thin kernel — 128-thread CTAs, no shared
+    memory, `num_ctas` of them — that shares SMs with the backward GEMMs instead of displacing their CTAs as the NCCL
+    kernel does (profiles/r02c_scaling_probe_n2.md). With multicast the adds happen inside the switch
+    (multimem.ld_reduce) and each rank moves 1/W of the bucket; otherwise W peer loads / stores per element."""
+
+    def __init__(self, group=None, min_bucket=32 * 1024 * 1024, num_ctas=16):
+        super().__init__(group, min_bucket=min_bucket, compress=None, overlap=True)
+        import torch.distributed._symmetric_memory as symm_mem
+        self._sm = symm_mem
+        self.group_obj = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(group)
+        self.num_ctas = num_ctas
+        self._bufs = []          # [(tensor, handle, peer_ptrs, mc_ptr)]
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group_obj.group_name)
+        except Exception:
+            pass
+
+    def alloc(self, numel, device, avoid=None):
+        """A zeroed flat fp32 buffer of `numel` elements in symmetric memory. COLLECTIVE on first use (every rank reaches
+        its first backward together). `avoid`: a buffer still aliased by live p.grad (gradient accumulation)."""
+        for ent in self._bufs:
+            t = ent[0]
+            if t.numel() == numel and (avoid is None or t.data_ptr() != avoid.data_ptr()):
+                t.zero_()
+                return t
+        t = self._sm.empty(numel, dtype=torch.float32, device=device)
+        hdl = self._sm.rendezvous(t, self.group_obj.group_name)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", lambda *a: False) and hdl.multicast_ptr else 0
+        self._bufs.append((t, hdl, ptrs, mc))
+        t.zero_()
+        return t
+
+    def _entry(self, flat):
+        for ent in self._bufs:
+            if ent[0].data_ptr() == flat.data_ptr():
+                return ent
+        return None
+
+    def uses_multicast(self):
+        return bool(self._bufs) and all(e[3] != 0 for e in self._bufs)
+
+    def _reduce_on_stream(self, sl):
+        ent = self._entry(self._G.flat)
+        if ent is None:                       # store not in symmetric memory (hand-built GradStore): NCCL
+            return super()._reduce_on_stream(sl)
+        t, hdl, ptrs, mc = ent
+        from . import ops
+        off = sl.storage_offset() - t.storage_offset()
+        hdl.barrier(channel=0)                # every rank's gradients of this bucket are final
+        ops.nvl_allreduce(ptrs, mc, self.world, self.rank, off, sl.numel(), 1.0 / self.world, self.num_ctas)
+        hdl.barrier(channel=1)                # every rank's slice has been written back everywhere
+
+
 def attach(model, group=None, overlap=True):
     """Make `model` exchange VTC features across the ranks of `group` and (overlap=True) average its gradients while
     the backward pass is still running (call after dist.init_process_group)."""
@@ -183,9 +244,23 @@ def attach(model, group=None, overlap=True):
     mode = os.environ.get("ALPRO_DP_OVERLAP", "1" if overlap else "0")    # 1: side stream, 0: one reduce at the end,
     compress = os.environ.get("ALPRO_GRAD_COMPRESS", "none")             # stream: bucketed on the compute stream
     compress = None if compress in ("none", "", "fp32") else compress
+    model.engine.grad_alloc = None
     if mode != "0":
-        model._grad_reducer = BucketedAllReduce(group, compress=compress, overlap=(mode != "stream"))
-        model.engine.grad_ready_hook = model._grad_reducer.ready
+        red = None
+        backend = os.environ.get("ALPRO_GRAD_REDUCER", "nvl")      # nvl: our peer-memory kernel, nccl: ncclAllReduce
+        if backend == "nvl" and mode != "stream" and compress is None and dist.get_backend(group) == "nccl":
+            try:
+                red = NvlGradReducer(group, num_ctas=int(os.environ.get("ALPRO_NVL_CTAS", "16")))
+                model.engine.grad_alloc = red.alloc
+            except Exception as e:             # no symmetric-memory support on this box: NCCL
+                import warnings
+                warnings.warn(f"alpro_b200: peer-memory gradient reducer unavailable ({type(e).__name__}: {e}); "
+                              "falling back to ncclAllReduce")
+                red = None
+        if red is None:
+            red = BucketedAllReduce(group, compress=compress, overlap=(mode != "stream"))
+        model._grad_reducer = red
+        model.engine.grad_ready_hook = red.ready
     else:
         model._grad_reducer = None
         model.engine.grad_ready_hook = None

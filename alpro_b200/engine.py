@@ -103,7 +103,9 @@ class GradStore:
     """One flat zero-initialised fp32 buffer with a view per parameter (single memset per backward).
     `groups` lists parameters that must be adjacent (BERT q|k|v) so that one fused wgrad GEMM can fill all three."""
 
-    def __init__(self, named_params, device, groups=()):
+    def __init__(self, named_params, device, groups=(), alloc=None):
+        """alloc(numel, device) -> zeroed flat fp32 tensor (data-parallel runs hand out symmetric memory that the
+        peer-memory gradient reducer can address on every rank); default: torch.zeros."""
         shapes = {n: tuple(p.shape) for n, p in named_params}
         order = []
         seen = set()
@@ -147,7 +149,7 @@ class GradStore:
             self.offsets[n] = (total, numel, shapes[n])
             total += numel if n in seen else (numel + 3) // 4 * 4
         self.regions.append((cur_lo, total, cur_tag))
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat = alloc(total, device) if alloc is not None else torch.zeros(total, dtype=torch.float32, device=device)
 
     def region_end(self, tag):
         for lo, hi, t in self.regions:
@@ -991,7 +993,11 @@ class AlproEngine:
         vtc_only = bool(ctx.get("vtc_only"))
         B, L, Nv, nt = ctx["B"], ctx["L"], ctx["Nv"], ctx["nt"]
         R, S_all = (0, 0) if vtc_only else (ctx["R"], ctx["S_all"])
-        G = GradStore(named_params, dev, bert_grad_groups("text_encoder.", cfg))
+        alloc = None
+        if getattr(self, "grad_alloc", None) is not None:
+            live = getattr(self, "grad_accum", None)            # a store still aliased by p.grad must not be recycled
+            alloc = lambda n, d: self.grad_alloc(n, d, avoid=live.flat if live is not None else None)
+        G = GradStore(named_params, dev, bert_grad_groups("text_encoder.", cfg), alloc=alloc)
         comm = self.comm
         dfo = None if vtc_only else torch.zeros(S_all * R, h, dtype=torch.float32, device=dev)   # d fusion output (scaled)
 

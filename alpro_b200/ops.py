@@ -394,3 +394,10 @@ def adamw_prepare(gnorm_sq, lr, beta1, beta2, correct_bias, step_count, step_siz
 def adamw_step_dev(p, g, m, v, beta1, beta2, eps, step_size_dev, lr_wd, gnorm_sq, max_norm):
     check(_L.alpro_adamw_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), beta1, beta2, eps, _p(step_size_dev), lr_wd,
                                   _p(gnorm_sq), max_norm, _s()), "alpro_adamw_step_dev")
+
+
+def nvl_allreduce(peer_ptrs, mc_ptr, world, rank, offset, count, scale, num_ctas=16):
+    """peer_ptrs: list of `world` integer device addresses (peer-mapped bases); mc_ptr: multicast address or 0."""
+    arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
+    check(_L.alpro_nvl_allreduce(ctypes.cast(arr, ctypes.c_void_p), int(mc_ptr) if mc_ptr else None, world, rank,
+                                 offset, count, scale, num_ctas, _s()), "alpro_nvl_allreduce")

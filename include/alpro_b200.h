@@ -272,6 +272,17 @@ int alpro_comm_reduce_scatter(void* comm, const void* send, void* recv, int64_t 
 /* buf[count] = sum (average != 0: mean) over ranks, in place */
 int alpro_comm_allreduce(void* comm, void* buf, int64_t count, int dtype, int average, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Gradient averaging as a thin kernel over NVLink peer memory (alpro_b200/csrc/allreduce.cu): 128-thread CTAs without
+ * shared memory that co-reside with the backward GEMMs. buf[offset, offset+count) (floats, offset % 4 == 0) is replaced
+ * on EVERY rank by scale * (sum over ranks); this call reduces and broadcasts the 1/world slice owned by `rank`.
+ * peer_ptrs: host array of `world` (<= 16) peer-mapped device pointers to each rank's buffer base; mc_ptr: NVSwitch
+ * multicast mapping of the same buffer (in-switch reduction, multimem.ld_reduce / multimem.st) or null (P2P loads and
+ * stores). The caller brackets the launch with a cross-rank barrier on the same stream.
+ */
+int alpro_nvl_allreduce(const void* const* peer_ptrs, void* mc_ptr, int world, int rank, int64_t offset, int64_t count,
+                        float scale, int num_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
