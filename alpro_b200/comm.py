@@ -230,10 +230,113 @@ class NvlGradReducer(BucketedAllReduce):
             return super()._reduce_on_stream(sl)
         t, hdl, ptrs, mc = ent
         from . import ops
-        off = sl.storage_offset() - t.storage_offset()
+        off = (sl.data_ptr() - ptrs[self.rank]) // 4      # floats from the base of the symmetric allocation
         hdl.barrier(channel=0)                # every rank's gradients of this bucket are final
         ops.nvl_allreduce(ptrs, mc, self.world, self.rank, off, sl.numel(), 1.0 / self.world, self.num_ctas)
         hdl.barrier(channel=1)                # every rank's slice has been written back everywhere
+
+
+class CeGradReducer(NvlGradReducer):
+    """Gradient averaging with NO resident kernel at all: the bytes move by the copy engines.
+
+    Rank r owns the r-th 1/W of every bucket. Per bucket, on the side stream: barrier (bucket final everywhere), W-1
+    cudaMemcpyAsync PULLS of the peers' copies of the owned slice into a staging buffer (NVLink, copy engines). The sum
+    `own = (own + sum staged) / W` is an ordinary full-width kernel placed IN ORDER on the compute stream one bucket
+    later (its inputs have long arrived, so the compute stream does not stall and nothing runs concurrently with the
+    GEMMs); after it, W-1 PUSHES of the averaged slice to the peers, again on the side stream. One closing barrier in
+    finish(). Motivation and numbers: profiles/r02c_scaling_probe_n2.md, r02d."""
+
+    def __init__(self, group=None, min_bucket=32 * 1024 * 1024):
+        super().__init__(group, min_bucket=min_bucket)
+        self._stage = [None, None]
+        self._pending = None            # (lo, hi, k, pulled_event) of the bucket whose sum has not been enqueued
+        self._summed = {}               # k -> event: sum of bucket k done (staging buffer k % 2 reusable)
+        self._k = 0
+
+    def _slice(self, lo, hi):
+        n4 = (hi - lo + 3) // 4
+        c4 = (n4 + self.world - 1) // self.world
+        a = min(n4, self.rank * c4)
+        b = min(n4, a + c4)
+        return lo + 4 * a, 4 * (b - a), 4 * c4
+
+    def _reduce(self, flat, lo, hi):
+        if hi <= lo:
+            return
+        ent = self._entry(flat)
+        if ent is None or self._gloo:
+            return BucketedAllReduce._reduce(self, flat, lo, hi)
+        from . import ops
+        t, hdl, ptrs, mc = ent
+        self.bytes += (hi - lo) * 4
+        k = self._k
+        self._k += 1
+        start, n_own, cap = self._slice(lo, hi)
+        slot = k & 1
+        need = cap * max(self.world - 1, 1)
+        if self._stage[slot] is None or self._stage[slot].numel() < need:
+            self._stage[slot] = torch.empty(need, dtype=torch.float32, device=flat.device)
+        ev = torch.cuda.Event()
+        ev.record()                                   # bucket k complete on the compute stream
+        # the previous bucket's sum goes onto the compute stream NOW (its pulls were issued one bucket ago)
+        self._flush_pending(ptrs, t)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            if (k - 2) in self._summed:               # staging slot reuse: its last consumer has run
+                self.side.wait_event(self._summed.pop(k - 2))
+            hdl.barrier(channel=0)                    # every rank's gradients of bucket k are final
+            pulled = torch.cuda.Event()
+            if n_own > 0:
+                off_b = (t.data_ptr() - ptrs[self.rank]) + start * 4     # bytes from the base of the allocation
+                j = 0
+                for p in range(self.world):
+                    if p == self.rank:
+                        continue
+                    ops.memcpy_async(self._stage[slot].data_ptr() + j * cap * 4, ptrs[p] + off_b, n_own * 4)
+                    j += 1
+            pulled.record()
+        self._pending = (start, n_own, cap, k, pulled, slot)
+
+    def _flush_pending(self, ptrs, t):
+        if self._pending is None:
+            return
+        from . import ops
+        start, n_own, cap, k, pulled, slot = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream()
+        cur.wait_event(pulled)
+        if n_own > 0:
+            ops.sum_slices(t[start:start + n_own], self._stage[slot], self.world - 1, n_own, cap, 1.0 / self.world)
+        done = torch.cuda.Event()
+        done.record()
+        self._summed[k] = done
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(done)
+            if n_own > 0:
+                off_b = (t.data_ptr() - ptrs[self.rank]) + start * 4
+                for p in range(self.world):
+                    if p != self.rank:
+                        ops.memcpy_async(ptrs[p] + off_b, ptrs[self.rank] + off_b, n_own * 4)
+
+    def finish(self):
+        G = self._G
+        if G is None:
+            raise RuntimeError("no gradients to reduce: run loss.backward() first")
+        if self._done < G.flat.numel():
+            self._reduce(G.flat, self._done, G.flat.numel())
+            self._done = G.flat.numel()
+        ent = self._entry(G.flat)
+        if ent is not None and not self._gloo:
+            t, hdl, ptrs, mc = ent
+            self._flush_pending(ptrs, t)
+            with torch.cuda.stream(self.side):
+                hdl.barrier(channel=1)                # every rank's pushes have landed everywhere
+            self._summed.clear()
+            self._k = 0
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self._G = None
+        return self.bytes
 
 
 def attach(model, group=None, overlap=True):
@@ -247,10 +350,14 @@ def attach(model, group=None, overlap=True):
     model.engine.grad_alloc = None
     if mode != "0":
         red = None
-        backend = os.environ.get("ALPRO_GRAD_REDUCER", "nvl")      # nvl: our peer-memory kernel, nccl: ncclAllReduce
-        if backend == "nvl" and mode != "stream" and compress is None and dist.get_backend(group) == "nccl":
+        # nccl: ncclAllReduce buckets on a side stream (round 1); nvl: our multimem / P2P kernel; ce: copy engines
+        backend = os.environ.get("ALPRO_GRAD_REDUCER", "nccl")
+        if backend in ("nvl", "ce") and mode != "stream" and compress is None and dist.get_backend(group) == "nccl":
             try:
-                red = NvlGradReducer(group, num_ctas=int(os.environ.get("ALPRO_NVL_CTAS", "16")))
+                if backend == "nvl":
+                    red = NvlGradReducer(group, num_ctas=int(os.environ.get("ALPRO_NVL_CTAS", "64")))
+                else:
+                    red = CeGradReducer(group)
                 model.engine.grad_alloc = red.alloc
             except Exception as e:             # no symmetric-memory support on this box: NCCL
                 import warnings

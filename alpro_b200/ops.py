@@ -401,3 +401,11 @@ def nvl_allreduce(peer_ptrs, mc_ptr, world, rank, offset, count, scale, num_ctas
     arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in peer_ptrs])
     check(_L.alpro_nvl_allreduce(ctypes.cast(arr, ctypes.c_void_p), int(mc_ptr) if mc_ptr else None, world, rank,
                                  offset, count, scale, num_ctas, _s()), "alpro_nvl_allreduce")
+
+
+def sum_slices(own, stage, nparts, count, part_stride, scale):
+    check(_L.alpro_sum_slices(_p(own), _p(stage), nparts, count, part_stride, scale, _s()), "alpro_sum_slices")
+
+
+def memcpy_async(dst_ptr, src_ptr, nbytes):
+    check(_L.alpro_memcpy_async(int(dst_ptr), int(src_ptr), nbytes, _s()), "alpro_memcpy_async")

@@ -282,6 +282,11 @@ int alpro_comm_allreduce(void* comm, void* buf, int64_t count, int dtype, int av
  */
 int alpro_nvl_allreduce(const void* const* peer_ptrs, void* mc_ptr, int world, int rank, int64_t offset, int64_t count,
                         float scale, int num_ctas, void* stream);
+/* copy-engine variant of the same reduction (comm.CeGradReducer): peers' slices are pulled into `stage`
+ * ([nparts] x part_stride floats) with alpro_memcpy_async, then own[0,count) = (own + sum_k stage[k]) * scale */
+int alpro_sum_slices(float* own, const float* stage, int nparts, int64_t count, int64_t part_stride, float scale,
+                     void* stream);
+int alpro_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

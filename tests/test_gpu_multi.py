@@ -114,16 +114,16 @@ def test_c_abi_communicator_two_ranks():
     assert got[0][1] > 0 and got[1][1] > 0
 
 
-def _nvl_worker(rank, world, port, q):
+def _nvl_worker(rank, world, port, q, backend="nvl"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    from alpro_b200.comm import NvlGradReducer
+    from alpro_b200.comm import CeGradReducer, NvlGradReducer
     res = {}
     try:
-        red = NvlGradReducer(min_bucket=1 << 18, num_ctas=8)
+        red = NvlGradReducer(min_bucket=1 << 18, num_ctas=8) if backend == "nvl" else CeGradReducer(min_bucket=1 << 18)
         n = (1 << 22) + 4 * 37            # not a multiple of the per-rank chunk
         t = red.alloc(n, dev)
         assert float(t.abs().max()) == 0.0
@@ -158,14 +158,16 @@ def _nvl_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_peer_memory_gradient_reducer_matches_nccl():
-    """csrc/allreduce.cu through comm.NvlGradReducer: bucketed in-place average over symmetric memory == ncclAllReduce
-    (fp32 rounding order aside), identical on every rank."""
+@pytest.mark.parametrize("backend", ["nvl", "ce"])
+def test_peer_memory_gradient_reducer_matches_nccl(backend):
+    """csrc/allreduce.cu through comm.NvlGradReducer (multimem / P2P kernel) and comm.CeGradReducer (copy engines + sum
+    kernel): bucketed in-place average over symmetric memory == ncclAllReduce (fp32 rounding order aside), identical
+    on every rank."""
     import torch.multiprocessing as mp
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nvl_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nvl_worker, args=(r, world, port, q, backend)) for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=600)
