@@ -194,10 +194,13 @@ class NvlGradReducer(BucketedAllReduce):
         self.rank = dist.get_rank(group)
         self.num_ctas = num_ctas
         self._bufs = []          # [(tensor, handle, peer_ptrs, mc_ptr)]
-        try:
-            symm_mem.enable_symm_mem_for_group(self.group_obj.group_name)
-        except Exception:
-            pass
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:                                  # needed by older torch, a deprecated no-op from 2.9 on
+                symm_mem.enable_symm_mem_for_group(self.group_obj.group_name)
+            except Exception:
+                pass
 
     def alloc(self, numel, device, avoid=None):
         """A zeroed flat fp32 buffer of `numel` elements in symmetric memory. COLLECTIVE on first use (every rank reaches
@@ -246,7 +249,7 @@ class CeGradReducer(NvlGradReducer):
     GEMMs); after it, W-1 PUSHES of the averaged slice to the peers, again on the side stream. One closing barrier in
     finish(). Motivation and numbers: profiles/r02c_scaling_probe_n2.md, r02d."""
 
-    def __init__(self, group=None, min_bucket=32 * 1024 * 1024):
+    def __init__(self, group=None, min_bucket=16 * 1024 * 1024):
         super().__init__(group, min_bucket=min_bucket)
         self._stage = [None, None]
         self._pending = None            # (lo, hi, k, pulled_event) of the bucket whose sum has not been enqueued
@@ -351,7 +354,7 @@ def attach(model, group=None, overlap=True):
     if mode != "0":
         red = None
         # nccl: ncclAllReduce buckets on a side stream (round 1); nvl: our multimem / P2P kernel; ce: copy engines
-        backend = os.environ.get("ALPRO_GRAD_REDUCER", "nccl")
+        backend = os.environ.get("ALPRO_GRAD_REDUCER", "ce")
         if backend in ("nvl", "ce") and mode != "stream" and compress is None and dist.get_backend(group) == "nccl":
             try:
                 if backend == "nvl":
