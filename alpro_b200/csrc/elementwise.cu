@@ -31,6 +31,26 @@ __global__ void cast_f32_to_16_kernel(const float* __restrict__ src, uint16_t* _
   }
 }
 
+// Batched form for the once-per-step refresh of every 16-bit weight operand (OperandCache.refresh): `table` holds one
+// (src, dst, count) triple per chunk of at most CAST_CHUNK elements (count % 4 == 0 except for a tensor's last chunk);
+// one block per chunk, so ~200 per-tensor launches become one.
+constexpr int CAST_CHUNK = 16384;
+__global__ void __launch_bounds__(256) cast_multi_kernel(const long long* __restrict__ table, int fmt) {
+  const long long* e = table + 3LL * blockIdx.x;
+  const float* __restrict__ src = reinterpret_cast<const float*>(e[0]);
+  uint16_t* __restrict__ dst = reinterpret_cast<uint16_t*>(e[1]);
+  const int n = static_cast<int>(e[2]);
+  const int n4 = n >> 2;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uint2 w;
+    w.x = pack2_16(v.x, v.y, fmt);
+    w.y = pack2_16(v.z, v.w, fmt);
+    reinterpret_cast<uint2*>(dst)[i] = w;
+  }
+  for (int j = (n4 << 2) + threadIdx.x; j < n; j += 256) dst[j] = f32_to_16(src[j], fmt);
+}
+
 // ------------------------------------------------------------------------------------------------ dropout mask
 // out[i] = keep_i / (1 - p) with keep_i ~ Bernoulli(1 - p) from the counter hash (nn.Dropout, xbert.py:178,331,358,436)
 __global__ void dropout_mask_kernel(uint16_t* __restrict__ out, int fmt, long long n, uint32_t thr, float scale,
@@ -817,6 +837,14 @@ extern "C" int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int 
   cast_f32_to_16_kernel<<<grid_for(cdiv(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<uint16_t*>(dst), n, fmt);
   ALPRO_CHECK_LAUNCH("alpro_cast_f32_to_16");
+  return 0;
+}
+
+extern "C" int alpro_cast_f32_to_16_multi(const int64_t* table, int num_chunks, int fmt, void* stream) {
+  ALPRO_REQUIRE(table && num_chunks > 0, "alpro_cast_f32_to_16_multi: bad args");
+  cast_multi_kernel<<<static_cast<unsigned>(num_chunks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(table), fmt);
+  ALPRO_CHECK_LAUNCH("alpro_cast_f32_to_16_multi");
   return 0;
 }
 

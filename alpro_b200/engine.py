@@ -39,6 +39,8 @@ class OperandCache:
         self.dtype = dtype
         self._c = {}
         self._epoch = 0
+        self._plain = {}       # name -> (parameter, 16-bit copy): entries that are a straight cast (batched refresh)
+        self._table = None     # (signature, device int64 chunk table, number of chunks)
 
     def _key(self, ps):
         # frozen parameters (the pretraining teacher) are never touched by an optimizer: version counter only
@@ -47,6 +49,37 @@ class OperandCache:
     def invalidate(self):
         """Force a refresh of every operand copy (used after an out-of-band parameter update, e.g. FusedAdamW)."""
         self._epoch += 1
+
+    def refresh(self):
+        """invalidate() + re-cast every straight-cast operand seen so far with ONE launch (alpro_cast_f32_to_16_multi)
+        instead of one per tensor on its next use (~200 launches per training step). Composed operands (W_fc W_proj)
+        and tensors that appeared since the table was built refresh lazily as before."""
+        self._epoch += 1
+        if not self._plain:
+            return
+        live = {n: (p, d) for n, (p, d) in self._plain.items() if p.requires_grad}
+        if not live:
+            return
+        sig = tuple((n, p.data_ptr(), d.data_ptr(), p.numel()) for n, (p, d) in live.items())
+        if self._table is None or self._table[0] != sig:
+            rows = []
+            for n, (p, d) in live.items():
+                src, dst, numel = p.data_ptr(), d.data_ptr(), p.numel()
+                if src % 16 or dst % 8 or not p.is_contiguous():
+                    self._table = None
+                    return                      # unusual layout: leave everything to the lazy path
+                for o in range(0, numel, ops.CAST_CHUNK):
+                    rows.append((src + 4 * o, dst + 2 * o, min(ops.CAST_CHUNK, numel - o)))
+            dev = next(iter(live.values()))[1].device
+            self._table = (sig, torch.tensor(rows, dtype=torch.int64).to(dev), len(rows))
+        ops.cast16_multi(self._table[1], self._table[2], ops._FMT[self.dtype])
+        for n, (p, d) in live.items():          # mark fresh: the next get() is a hit
+            ent = self._c.get(n)
+            if ent is not None and ent[1] is d:
+                self._c[n] = (self._key((p,)), d)
+            else:                               # a row slice of a concatenated operand (fused q|k|v)
+                self._fresh_parts = getattr(self, "_fresh_parts", {})
+                self._fresh_parts[n] = self._epoch
 
     def get(self, name, p, shape2d=None):
         ent = self._c.get(name)
@@ -57,6 +90,8 @@ class OperandCache:
             ops.cast16(src.contiguous().view(-1), dst.view(-1))
             ent = (key, dst)
             self._c[name] = ent
+            if src.is_contiguous():
+                self._plain[name] = (p, dst)
         return ent[1]
 
     def get_fused_linear(self, name, w2, w1, b1):
@@ -88,9 +123,18 @@ class OperandCache:
             rows = sum(p.shape[0] for p in ps)
             if ps[0].dim() == 2:
                 dst = ent[1] if ent is not None else _empty((rows, ps[0].shape[1]), self.dtype, ps[0].device)
+                fresh = getattr(self, "_fresh_parts", {})
                 r = 0
-                for p in ps:
-                    ops.cast16(p.detach().contiguous().view(-1), dst[r:r + p.shape[0]].view(-1))
+                for i, p in enumerate(ps):
+                    part = dst[r:r + p.shape[0]]
+                    pname = f"{name}#{i}"
+                    reg = self._plain.get(pname)
+                    done = (reg is not None and reg[0] is p and reg[1].data_ptr() == part.data_ptr()
+                            and fresh.get(pname) == self._epoch)          # already re-cast by refresh() this epoch
+                    if not done:
+                        ops.cast16(p.detach().contiguous().view(-1), part.view(-1))
+                    if p.is_contiguous():
+                        self._plain[pname] = (p, part)
                     r += p.shape[0]
             else:
                 dst = torch.cat([p.detach() for p in ps]).contiguous()
@@ -795,7 +839,7 @@ class AlproEngine:
         save = need_grad
         comm = self.comm
         if need_grad:
-            self.W.invalidate()      # a training step never trusts operand copies made before it (see OperandCache)
+            self.W.refresh()         # a training step never trusts operand copies made before it (see OperandCache)
         ops.clamp_scalar(P["temp"].detach(), 0.001, 0.5)                       # temp.clamp_ :80-81 / :734-735
         frames = batch["visual_inputs"]
         B = frames.shape[0]

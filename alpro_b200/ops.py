@@ -147,6 +147,13 @@ def cast16(src, dst):
     check(_L.alpro_cast_f32_to_16(_p(src), _p(dst), src.numel(), _fmt(dst), _s()), "alpro_cast_f32_to_16")
 
 
+CAST_CHUNK = 16384
+
+
+def cast16_multi(table, num_chunks, fmt):
+    check(_L.alpro_cast_f32_to_16_multi(_p(table), num_chunks, fmt, _s()), "alpro_cast_f32_to_16_multi")
+
+
 def layernorm_fwd(x, gamma, beta, eps, out32=None, out16=None, mean=None, rstd=None, mul16=None):
     M, d = x.shape
     check(_L.alpro_layernorm_fwd(_p(x), x.stride(0), _p(gamma), _p(beta), eps, M, d, _p(out32),

@@ -91,6 +91,10 @@ int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, 
  */
 /* fp32 -> 16-bit cast of a contiguous buffer (weight operand copies; replaces nothing in the reference, which runs fp32) */
 int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int fmt, void* stream);
+/* the same cast for MANY tensors in one launch: `table` (device, int64) holds num_chunks triples (src address, dst
+ * address, element count <= 16384); src chunks 16-byte aligned, dst chunks 8-byte aligned. Used for the once-per-step
+ * refresh of all 16-bit weight operands. */
+int alpro_cast_f32_to_16_multi(const int64_t* table, int num_chunks, int fmt, void* stream);
 
 /* LayerNorm over the last dim (nn.LayerNorm: vit.py:113,119,127,279 eps 1e-6; xbert.py:177,354,433,658 eps 1e-12).
  * x fp32 [M,d] -> out32 (optional) and/or out16 (optional); per-row mean / rstd saved for the backward. d%4==0, d<=1024.
