@@ -12,6 +12,7 @@
 //
 // Backward kernels recompute the probabilities from the saved log-sum-exp (no SxS tensor ever reaches HBM).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -337,6 +338,7 @@ struct SAttnParams {
   // train-mode attention-probability dropout (BertSelfAttention.dropout, xbert.py:331): 0 = off
   uint32_t drop_thr, drop_seed;
   float drop_scale;
+  int cls_last;          // TMA kernels: tile row S-1 holds token 0 (the strided tokens 1..S-1 are ONE tensor-map box)
   long long* trace;      // diagnostics (ALPRO_ATTN_TRACE=1): 64 clock64() stamps per CTA, null in normal runs
   int stagger;           // tcgen05 backward: first-wave CTA i starts (i % 4) * stagger cycles late (0 = off)
 };
@@ -821,8 +823,19 @@ __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) 
     if (p.trace && (cond))                                                                               \
       p.trace[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (slot)] = clock64() - t_start; \
   } while (0)
-template <bool BF, bool DROP, bool MASK>
-__global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams p) {
+// TMA = true (r02): the operand tiles arrive by tensor-map loads instead of the per-thread cp.async gather. The strided
+// token rows of one sequence (row = clip*clip_rows + 1 + frame + (j-1)*stride) are ONE box of a 4-D map
+// (column, token, frame, clip) over the qkv matrix, written by the TMA unit straight into the 128B-swizzled K-major
+// layout: one elected thread issues three instructions where 256 threads issued ~4600 predicated 16-byte copies with
+// their address arithmetic (3.1 k of the CTA's 24 k cycles, profiles/r01p_sattn_tc_traces.md). The shared cls token
+// is not part of that box; it is placed LAST (tile row S-1, cp.async by 8 threads) so that the box lands at the
+// 1024-byte-aligned tile base: attention is invariant under a common permutation of keys/queries, only the row <->
+// token map of the mask, the log-sum-exp and the output rows changes (tok()).
+template <bool BF, bool DROP, bool MASK, bool TMA>
+__global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmAll,
+                                                              const __grid_constant__ CUtensorMap tmQ0,
+                                                              const __grid_constant__ CUtensorMap tmQ1,
+                                                              const SAttnParams p) {
   const long long t_start = p.trace ? clock64() : 0;
   extern __shared__ uint8_t sm_raw[];
   const uint32_t raw_addr = smem_u32(sm_raw);
@@ -839,17 +852,30 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams 
   float* sMask = reinterpret_cast<float*>(sP + 2 * 16384);
   float* sStat = sMask + 256;          // [2][128] row maxima, then [2][128] row sums of the two column halves
   uint64_t* bar = reinterpret_cast<uint64_t*>(sStat + 512);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* ldbar = bar + 1;           // TMA: K, V and the first query tile have landed
+  uint64_t* qbar = bar + 2;            // TMA: the next query tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   // Two threads per query row: warp w and warp w + 4 share TMEM lane quarter w % 4; group `wg` takes the 32-key chunks
   // with (chunk & 1) == wg, and columns [32 wg, 32 wg + 32) of the output row.
   const int wg = warp >> 2, lq = warp & 3;
   const int rit = lq * 32 + lane;      // row inside the query tile = TMEM lane
+  // tile row -> token of the sequence (identity unless the cls token sits last)
+  const bool cls_last = TMA && p.cls_last;
+  auto tok = [&](int j) { return cls_last ? (j == S - 1 ? 0 : j + 1) : j; };
+  const int n_box = cls_last ? S - 1 : S;                       // rows delivered by the tensor-map boxes
+  const int c_t = seq % p.seq_div, c_b = seq / p.seq_div;       // frame / clip coordinates of the 4-D map
 
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(ldbar, 1);
+    mbar_init(qbar, 1);
     fence_barrier_init();
+    if (TMA) {
+      tma_prefetch_desc(&tmAll);
+      tma_prefetch_desc(&tmQ0);
+    }
   }
   if (warp == 0) {
     __syncwarp();
@@ -875,13 +901,43 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams 
                    : "memory");
     }
   };
-  gather(p.d + head * DH, 0, S32, sK);
-  gather(head * DH, 0, 128, sQ);
-  gather(2 * p.d + head * DH, 0, S32, sV);
-  sMask[tid] = tid < S ? (p.mask ? p.mask[static_cast<long long>(seq) * S + tid] * LOG2E : 0.f) : -INFINITY;
+  // one 16-byte chunk of the cls token's row (token 0 lives at the clip's base row) -> tile row `trow_` of `tile`
+  auto cls_chunk = [&](int col0, uint8_t* tile, int trow_, int c8) {
+    const uint16_t* src = p.qkv + rows.base * p.ld_qkv + col0 + c8 * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile) + trow_ * 128 +
+                                                                   ((c8 ^ (trow_ & 7)) << 4)), "l"(src) : "memory");
+  };
+  if (TMA) {
+    __syncthreads();                   // barrier initialisation visible before the first arrive / complete_tx
+    if (tid == 0) {
+      const int q0 = min(128, n_box);
+      mbar_arrive_expect_tx(ldbar, static_cast<uint32_t>((2 * n_box + q0) * 128));
+      tma_load_4d(sK, &tmAll, ldbar, p.d + head * DH, 0, c_t, c_b);
+      tma_load_4d(sQ, &tmQ0, ldbar, head * DH, 0, c_t, c_b);
+      tma_load_4d(sV, &tmAll, ldbar, 2 * p.d + head * DH, 0, c_t, c_b);
+    }
+    // rows the boxes do not write: the cls token (last valid row) and the zero padding up to S32 (padded keys are
+    // masked with -inf, but 0 * NaN of stale shared memory would still poison P V)
+    if (cls_last) {
+      if (tid < 8) cls_chunk(p.d + head * DH, sK, S - 1, tid);
+      else if (tid < 16) cls_chunk(2 * p.d + head * DH, sV, S - 1, tid - 8);
+      else if (tid < 24 && S - 1 < 128) cls_chunk(head * DH, sQ, S - 1, tid - 16);
+    }
+    for (int i = tid; i < (S32 - S) * 16; i += 256) {            // (S32 - S) rows x 8 chunks x {K, V}
+      const int rr = S + (i >> 4), c8 = i & 7;
+      uint8_t* tile = (i & 8) ? sV : sK;
+      *reinterpret_cast<uint4*>(tile + rr * 128 + (c8 << 4)) = make_uint4(0u, 0u, 0u, 0u);   // all-zero row: any swizzle
+    }
+  } else {
+    gather(p.d + head * DH, 0, S32, sK);
+    gather(head * DH, 0, 128, sQ);
+    gather(2 * p.d + head * DH, 0, S32, sV);
+  }
+  sMask[tid] = tid < S ? (p.mask ? p.mask[static_cast<long long>(seq) * S + tok(tid)] * LOG2E : 0.f) : -INFINITY;
   ATTN_TRACE(tid == 0, 1);
   cp_async_wait_all();
   fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+  if (TMA) mbar_wait(ldbar, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -913,7 +969,18 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams 
     tc_fence_after();
     ATTN_TRACE(tid == 0 && qt < 2, 4 + 10 * qt);
     const bool more = (qt + 1) * 128 < S;
-    if (more) gather(head * DH, (qt + 1) * 128, 128, sQ);   // sQ is free again: next query tile lands under the softmax
+    if (more) {                        // sQ is free again: next query tile lands under the softmax
+      if (TMA) {
+        const int lo = (qt + 1) * 128;
+        if (tid == 0 && n_box > lo) {
+          mbar_arrive_expect_tx(qbar, static_cast<uint32_t>((n_box - lo) * 128));
+          tma_load_4d(sQ, &tmQ1, qbar, head * DH, lo, c_t, c_b);
+        }
+        if (cls_last && tid < 8 && S - 1 >= lo) cls_chunk(head * DH, sQ, S - 1 - lo, tid);
+      } else {
+        gather(head * DH, (qt + 1) * 128, 128, sQ);
+      }
+    }
 
     const int row = qt * 128 + rit;    // query row owned by this thread (shared with its partner in the other group)
     // ---- pass 1: maximum over this thread's chunks (base-2 domain, 4 independent chains), then over both groups
@@ -1041,7 +1108,7 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams 
         w.w = pack2<BF>(__uint_as_float(r[q4 * 8 + 6]) * inv, __uint_as_float(r[q4 * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(myrow + (((wg * 4 + q4) ^ (rit & 7)) << 4)) = w;
       }
-      if (wg == 0 && row < S && p.lse) p.lse[(static_cast<long long>(seq) * p.heads + head) * S + row] = m + log2f(l);
+      if (wg == 0 && row < S && p.lse) p.lse[(static_cast<long long>(seq) * p.heads + head) * S + tok(row)] = m + log2f(l);
       tc_fence_before();
       __syncthreads();
 #pragma unroll
@@ -1050,8 +1117,9 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams 
         const int jj = qt * 128 + rr;
         const uint4 v = *reinterpret_cast<const uint4*>(sP + rr * 128 + swz);
         if (jj < S) {
-          uint16_t* dst = (jj == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
-                                               : p.o + rows(jj) * p.ld_o + head * DH;
+          const int tk = tok(jj);
+          uint16_t* dst = (tk == 0 && p.cls_o) ? p.cls_o + static_cast<long long>(seq) * p.d + head * DH
+                                               : p.o + rows(tk) * p.ld_o + head * DH;
           *reinterpret_cast<uint4*>(dst + ch * 8) = v;
         }
       }
@@ -1060,6 +1128,7 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams 
     if (more) {
       cp_async_wait_all();             // next query tile has landed
       fence_proxy_async();
+      if (TMA && n_box > (qt + 1) * 128) mbar_wait(qbar, static_cast<uint32_t>(qt & 1));
     }
     tc_fence_before();
     __syncthreads();                   // every thread is done with TMEM / sP before the next tile reuses them
@@ -1093,8 +1162,13 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const SAttnParams 
 // MMAs of step s-1) while the softmax warps transform step s.
 // Shared memory: Q, dO [S16][64]; K, V [nkt*128][64] (zero rows beyond S); P^T ring 2 atoms; dS^T 4 atoms (one per query
 // chunk of the current key tile) -> ~215 KB at S=197, one CTA per SM; S <= 240.
-template <bool BF, bool DROP>
-__global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams p) {
+// TMA = true (r02): Q, dO, K, V arrive as four tensor-map boxes issued by one thread (see the forward kernel for the
+// map and the cls-last tile order); the per-thread gather took 8 k cycles just to ISSUE its ~7 k predicated copies
+// (profiles/r01p_sattn_tc_traces.md: "loads issued" at 7951 of 31 k cycles).
+template <bool BF, bool DROP, bool TMA>
+__global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                              const __grid_constant__ CUtensorMap tmDO,
+                                                              const SAttnParams p) {
   const long long t_start = p.trace ? clock64() : 0;
   extern __shared__ uint8_t sm_raw[];
   const uint32_t raw_addr = smem_u32(sm_raw);
@@ -1123,10 +1197,25 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
   uint64_t* g_done = bars + 6;         // [2] MMA -> softmax: gradient MMAs of the step retired (staging reusable)
   uint64_t* acc_full = bars + 8;       //     MMA -> softmax: dV/dK of the key tile complete
   uint64_t* acc_free = bars + 9;       //     softmax -> MMA: dV/dK read out (8 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* ld_bar = bars + 10;        //     TMA: the four operand boxes have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role branches stay uniform
   constexpr int fmt = BF ? 1 : 0;
+  // tile row -> token (identity unless the shared cls token sits last, see the forward kernel)
+  const bool cls_last = TMA && p.cls_last;
+  auto tok = [&](int j) { return cls_last ? (j == S - 1 ? 0 : j + 1) : j; };
+  const int cls_row = cls_last ? S - 1 : 0;                  // tile row of token 0
+  const int n_box = cls_last ? S - 1 : S;
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(ld_bar, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+    }
+    __syncthreads();
+  }
   // One CTA per SM and every unit costs the same, so all SMs load, compute and store in lockstep: HBM idles while
   // they compute and is oversubscribed while they load. ALPRO_ATTN_STAGGER=<cycles> starts the first wave in four
   // phases so that the SMs stay out of step for the whole launch (experiment; off by default).
@@ -1171,28 +1260,62 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
                      : "memory");
       }
     };
-    gather(p.qkv, p.ld_qkv, head * DH, S16, sQ);
-    gather(p.dout, p.ld_o, head * DH, S16, sG);
-    gather(p.qkv, p.ld_qkv, p.d + head * DH, krows, sK);
-    gather(p.qkv, p.ld_qkv, 2 * p.d + head * DH, krows, sV);
+    if (TMA) {
+      const int c_t = seq % p.seq_div, c_b = seq / p.seq_div;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(ld_bar, static_cast<uint32_t>(4 * n_box * 128));
+        tma_load_4d(sQ, &tmQKV, ld_bar, head * DH, 0, c_t, c_b);
+        tma_load_4d(sG, &tmDO, ld_bar, head * DH, 0, c_t, c_b);
+        tma_load_4d(sK, &tmQKV, ld_bar, p.d + head * DH, 0, c_t, c_b);
+        tma_load_4d(sV, &tmQKV, ld_bar, 2 * p.d + head * DH, 0, c_t, c_b);
+      }
+      // token 0 (not part of the boxes): the eight threads that own tile row cls_row copy its four rows, so that the
+      // D computation below reads chunks this very thread has loaded
+      if (cls_last && r0 == (cls_row & 31)) {
+        const uint32_t off = cls_row * 128 + ((ch ^ (cls_row & 7)) << 4);
+        const uint16_t* q0 = p.qkv + rows.base * p.ld_qkv + head * DH + ch * 8;
+        const uint16_t* g0 = p.dout + rows.base * p.ld_o + head * DH + ch * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sQ) + off), "l"(q0) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sG) + off), "l"(g0) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sK) + off), "l"(q0 + p.d) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sV) + off), "l"(q0 + 2 * p.d) : "memory");
+      }
+      // rows no box writes: zero (all-zero rows look the same under any swizzle)
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = tid; i < (S16 - S) * 8; i += 256) {
+        *reinterpret_cast<uint4*>(sQ + (S + (i >> 3)) * 128 + ((i & 7) << 4)) = z;
+        *reinterpret_cast<uint4*>(sG + (S + (i >> 3)) * 128 + ((i & 7) << 4)) = z;
+      }
+      for (int i = tid; i < (krows - S) * 8; i += 256) {
+        *reinterpret_cast<uint4*>(sK + (S + (i >> 3)) * 128 + ((i & 7) << 4)) = z;
+        *reinterpret_cast<uint4*>(sV + (S + (i >> 3)) * 128 + ((i & 7) << 4)) = z;
+      }
+    } else {
+      gather(p.qkv, p.ld_qkv, head * DH, S16, sQ);
+      gather(p.dout, p.ld_o, head * DH, S16, sG);
+      gather(p.qkv, p.ld_qkv, p.d + head * DH, krows, sK);
+      gather(p.qkv, p.ld_qkv, 2 * p.d + head * DH, krows, sV);
+    }
     uint4 ov[8];   // this thread's chunks of the forward outputs O (for D_q = rowsum(dO_q * O_q))
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int row = r0 + 32 * u;
       ov[u] = make_uint4(0u, 0u, 0u, 0u);
       if (row < S) {
-        const uint16_t* orow = (row == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
-                                                            : p.o_fwd + rows(row) * p.ld_o + head * DH;
+        const int tk = tok(row);
+        const uint16_t* orow = (tk == 0 && p.seq_div > 1) ? p.cls_fwd + static_cast<long long>(seq) * p.d + head * DH
+                                                           : p.o_fwd + rows(tk) * p.ld_o + head * DH;
         ov[u] = *reinterpret_cast<const uint4*>(orow + ch * 8);
       }
     }
     {
       const int j = tid;   // 256 gather threads = 256 table entries
-      sMask[j] = j < S ? (p.mask ? p.mask[static_cast<long long>(seq) * S + j] * LOG2E : 0.f) : -INFINITY;
-      sNl[j] = j < S ? -p.lse[(static_cast<long long>(seq) * p.heads + head) * S + j] : -INFINITY;
+      sMask[j] = j < S ? (p.mask ? p.mask[static_cast<long long>(seq) * S + tok(j)] * LOG2E : 0.f) : -INFINITY;
+      sNl[j] = j < S ? -p.lse[(static_cast<long long>(seq) * p.heads + head) * S + tok(j)] : -INFINITY;
     }
     ATTN_TRACE(tid == 0, 1);
     cp_async_wait_all();
+    if (TMA) mbar_wait(ld_bar, 0);
     ATTN_TRACE(tid == 0, 2);
     // D from this thread's own chunks of dO (cp.async data of the issuing thread is visible after the wait). The
     // token-0 upstream gradient is rescaled in place first: the group's cls output was the (weighted) mean over frames.
@@ -1211,14 +1334,14 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
           float g0f, g1f, o0f, o1f;
           unpack2<BF>(gw[k], g0f, g1f);
           unpack2<BF>(ow[k], o0f, o1f);
-          if (row == 0 && p.seq_div > 1) {
+          if (row == cls_row && p.seq_div > 1) {
             gw[k] = pack2c<BF>(g0f * gscale0, g1f * gscale0);
             unpack2<BF>(gw[k], g0f, g1f);
           }
           dsum = fmaf(g0f, o0f, dsum);
           dsum = fmaf(g1f, o1f, dsum);
         }
-        if (row == 0 && p.seq_div > 1) *gp = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+        if (row == cls_row && p.seq_div > 1) *gp = make_uint4(gw[0], gw[1], gw[2], gw[3]);
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
         dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
@@ -1324,7 +1447,7 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
         __syncwarp();
         if (lane == 0) mbar_arrive(release);
       }
-      if (jbase + lane == 0 && fbase) {
+      if (jbase + lane == cls_row && fbase) {
         float* dst = p.dcls_qkv + static_cast<long long>(seq) * 3 * p.d + coff;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -1354,8 +1477,8 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const SAttnParams 
         const int rr = i * 4 + (lane >> 3);
         const int jj = jbase + rr;
         const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((c ^ (rr & 7)) << 4));
-        if (jj < S && !(jj == 0 && fbase))
-          *reinterpret_cast<uint4*>(p.dqkv + rows(jj) * p.ld_qkv + coff + c * 8) = v;
+        if (jj < S && !(jj == cls_row && fbase))
+          *reinterpret_cast<uint4*>(p.dqkv + rows(tok(jj)) * p.ld_qkv + coff + c * 8) = v;
       }
       __syncwarp();
     };
@@ -1624,6 +1747,58 @@ static long long* trace_buffer(size_t ctas, cudaStream_t st) {
   return g_trace;
 }
 
+// ---------------------------------------------------------------------------------------------- tensor maps (r02)
+typedef CUresult (*SeqEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static SeqEncodeFn seq_encode_fn() {
+  static SeqEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<SeqEncodeFn>(f);
+    return static_cast<SeqEncodeFn>(nullptr);
+  }();
+  return fn;
+}
+
+// 4-D map (column, token, frame, clip) over a row-major 16-bit matrix [rows, ld] holding the sequences of the
+// SAttnParams row rule: token i of the box is row  clip*clip_rows + first_row + frame + i*stride. Box = 64 columns x
+// box_rows tokens of one (frame, clip), 128-byte swizzle (= the UMMA K-major SW128 layout of a [box_rows][64] tile).
+static int make_seq_map(CUtensorMap* m, const uint16_t* mat, int64_t ld, int cols, int first_row, int n_tok, int stride,
+                        int seq_div, int groups, int64_t clip_rows, int box_rows) {
+  SeqEncodeFn enc = seq_encode_fn();
+  if (!enc) return ALPRO_ENOTSUP;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(n_tok),
+                        static_cast<cuuint64_t>(seq_div), static_cast<cuuint64_t>(groups)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(stride) * ld * 2, static_cast<cuuint64_t>(ld) * 2,
+                           static_cast<cuuint64_t>(clip_rows) * ld * 2};
+  cuuint32_t box[4] = {DH, static_cast<cuuint32_t>(box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  void* base = const_cast<uint16_t*>(mat + static_cast<int64_t>(first_row) * ld);
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(4d) failed (%d): cols=%d tok=%d div=%d groups=%d ld=%lld box=%d", (int)r, cols,
+                   n_tok, seq_div, groups, (long long)ld, box_rows);
+    return ALPRO_EINVAL;
+  }
+  return 0;
+}
+
+// Tensor-map path usable? (ALPRO_ATTN_TMA=0 switches it off; read per call so tests can compare both paths)
+static bool seq_tma_wanted(const SAttnParams& p) {
+  const char* e = getenv("ALPRO_ATTN_TMA");
+  if (e && e[0] == '0') return false;
+  if (!seq_encode_fn()) return false;
+  if (!aligned16(p.qkv) || (p.ld_qkv % 8) != 0 || 3 * p.d > p.ld_qkv || p.nseq % p.seq_div != 0) return false;
+  const bool cls_last = !(p.seq_div == 1 && p.stride == 1);
+  if (cls_last && (p.drop_thr != 0 || p.S < 2)) return false;   // dropout counters are defined in token order
+  return true;
+}
+
 static int fill_sattn(SAttnParams& p, const void* qkv, int64_t ld_qkv, const float* mask, int S, int nseq, int heads,
                       int fmt, int seq_div, int stride, int64_t clip_rows, float scale, float drop_p,
                       uint32_t drop_seed) {
@@ -1656,11 +1831,32 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
     const size_t S32 = (S + 31) & ~31;
     const size_t smem_tc = 1024 + 128 * 128 + S32 * 128 * 2 + 2 * 16384 + (256 + 512) * sizeof(float) + 64;
     p.trace = trace_buffer(static_cast<size_t>(heads) * nseq, st);
-#define LAUNCH_FWD_TC(BF, DR, MK)                                      \
-  do {                                                                 \
-    rc = set_smem(sattn_fwd_tc_kernel<BF, DR, MK>, smem_tc);           \
-    if (rc) return rc;                                                 \
-    sattn_fwd_tc_kernel<BF, DR, MK><<<grid, 256, smem_tc, st>>>(p);    \
+    CUtensorMap tmAll, tmQ0, tmQ1;
+    memset(&tmAll, 0, sizeof(tmAll));
+    bool tma = seq_tma_wanted(p);
+    if (tma) {
+      p.cls_last = !(seq_div == 1 && stride == 1);
+      const int n_box = p.cls_last ? S - 1 : S, first = p.cls_last ? 1 : 0, groups = nseq / seq_div;
+      rc = make_seq_map(&tmAll, p.qkv, ld_qkv, 3 * p.d, first, n_box, stride, seq_div, groups, clip_rows, n_box);
+      if (!rc) rc = make_seq_map(&tmQ0, p.qkv, ld_qkv, 3 * p.d, first, n_box, stride, seq_div, groups, clip_rows,
+                                 n_box < 128 ? n_box : 128);
+      if (!rc && n_box > 128)
+        rc = make_seq_map(&tmQ1, p.qkv, ld_qkv, 3 * p.d, first, n_box, stride, seq_div, groups, clip_rows, n_box - 128);
+      if (rc) { tma = false; p.cls_last = 0; rc = 0; }          // descriptor not encodable: per-thread gather
+      else if (n_box <= 128) tmQ1 = tmQ0;
+    }
+    if (!tma) tmQ0 = tmQ1 = tmAll;
+#define LAUNCH_FWD_TC(BF, DR, MK)                                                                   \
+  do {                                                                                              \
+    if (tma) {                                                                                      \
+      rc = set_smem(sattn_fwd_tc_kernel<BF, DR, MK, true>, smem_tc);                                \
+      if (rc) return rc;                                                                            \
+      sattn_fwd_tc_kernel<BF, DR, MK, true><<<grid, 256, smem_tc, st>>>(tmAll, tmQ0, tmQ1, p);      \
+    } else {                                                                                        \
+      rc = set_smem(sattn_fwd_tc_kernel<BF, DR, MK, false>, smem_tc);                               \
+      if (rc) return rc;                                                                            \
+      sattn_fwd_tc_kernel<BF, DR, MK, false><<<grid, 256, smem_tc, st>>>(tmAll, tmQ0, tmQ1, p);     \
+    }                                                                                               \
   } while (0)
 #define LAUNCH_FWD_TC_F(BF)                                                          \
   do {                                                                               \
@@ -1732,12 +1928,29 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
     }
     const size_t krows = static_cast<size_t>((S + 127) / 128) * 128;
     const size_t smem_tc = 1024 + 2 * static_cast<size_t>(S_pad) * 128 + 2 * krows * 128 + 6 * 16384 +
-                           3 * 256 * sizeof(float) + 10 * sizeof(uint64_t) + 16;
-#define LAUNCH_BWD_TC(BF, DR)                                          \
-  do {                                                                 \
-    rc = set_smem(sattn_bwd_tc_kernel<BF, DR>, smem_tc);               \
-    if (rc) return rc;                                                 \
-    sattn_bwd_tc_kernel<BF, DR><<<grid, 288, smem_tc, st>>>(p);        \
+                           3 * 256 * sizeof(float) + 11 * sizeof(uint64_t) + 16;
+    CUtensorMap tmQKV, tmDO;
+    memset(&tmQKV, 0, sizeof(tmQKV));
+    bool tma = seq_tma_wanted(p) && aligned16(dout);
+    if (tma) {
+      p.cls_last = !(seq_div == 1 && stride == 1);
+      const int n_box = p.cls_last ? S - 1 : S, first = p.cls_last ? 1 : 0, groups = nseq / seq_div;
+      rc = make_seq_map(&tmQKV, p.qkv, ld_qkv, 3 * p.d, first, n_box, stride, seq_div, groups, clip_rows, n_box);
+      if (!rc) rc = make_seq_map(&tmDO, p.dout, ld_o, p.d, first, n_box, stride, seq_div, groups, clip_rows, n_box);
+      if (rc) { tma = false; p.cls_last = 0; rc = 0; }
+    }
+    if (!tma) tmDO = tmQKV;
+#define LAUNCH_BWD_TC(BF, DR)                                                             \
+  do {                                                                                    \
+    if (tma) {                                                                            \
+      rc = set_smem(sattn_bwd_tc_kernel<BF, DR, true>, smem_tc);                          \
+      if (rc) return rc;                                                                  \
+      sattn_bwd_tc_kernel<BF, DR, true><<<grid, 288, smem_tc, st>>>(tmQKV, tmDO, p);      \
+    } else {                                                                              \
+      rc = set_smem(sattn_bwd_tc_kernel<BF, DR, false>, smem_tc);                         \
+      if (rc) return rc;                                                                  \
+      sattn_bwd_tc_kernel<BF, DR, false><<<grid, 288, smem_tc, st>>>(tmQKV, tmDO, p);     \
+    }                                                                                     \
   } while (0)
     if (fmt == 1) {
       if (p.drop_thr) LAUNCH_BWD_TC(true, true); else LAUNCH_BWD_TC(true, false);

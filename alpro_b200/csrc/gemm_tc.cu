@@ -491,6 +491,13 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
     } else if (mode == E_RESID_OUT32) {
       tma_epi = tma_epi && !p.out16 && aligned16(p.out32) && (p.ld32 % 4) == 0 && aligned16(p.resid) &&
                 (p.ldresid % 4) == 0;
+    } else if (mode == E_GENERIC && p.act == ALPRO_ACT_GELU_GRAD && p.resid && p.out32 && !p.out16 && !p.out16b &&
+               p.aux16 && !p.bias2 && p.skip_period == 0) {
+      // (acc + bias) * aux + resid — the dropout-mask form of the BERT output projections: the residual kernel with a
+      // multiplier tile (the generic epilogue of gemm_tc2.cu ran these at 257 / 845 TFLOP/s, r02g shape table)
+      tma_epi = tma_epi && aligned16(p.out32) && (p.ld32 % 4) == 0 && aligned16(p.resid) && (p.ldresid % 4) == 0 &&
+                aligned16(p.aux16) && (p.ldaux % 8) == 0 && (N % 16) == 0;
+      if (tma_epi) mode = E_RESID_OUT32;
     } else if (mode == E_ATOMIC) {   // split-K partial sums: TMA reduce-add instead of red.global per element
       tma_epi = tma_epi && aligned16(p.out32) && (p.ld32 % 4) == 0;
     } else {

@@ -113,8 +113,31 @@ __device__ __forceinline__ void chunk_math(const GemmKParams& p, const uint32_t 
 
 // E_RESID_OUT32: one 16-column fp32 chunk; the residual tile sits in buf (TMA-loaded), result written in place:
 //   out = resid + ra * acc + rb * bias      (rows that keep the plain residual arrive with ra = rb = 0)
+//   with a 16-bit multiplier tile (p.aux16: the hidden-dropout mask of BertSelfOutput / BertOutput, xbert.py:358,436):
+//   out = resid + (ra * acc + rb * bias) * aux      — the lane reads the 32 bytes of its own row straight from global
 __device__ __forceinline__ void chunk_resid(const GemmKParams& p, const uint32_t (&r)[16], int col0, int lane,
-                                            uint8_t* buf, const RowScale rs) {
+                                            uint8_t* buf, const RowScale rs, long long row) {
+  if (p.aux16) {   // warp-uniform
+    const uint4* ap = reinterpret_cast<const uint4*>(p.aux16 + row * p.ldaux + col0);
+    const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+    const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * g));
+      float4 x = *reinterpret_cast<const float4*>(buf + stage_off(lane, g));
+      const float m0 = f16_to_32(static_cast<uint16_t>(aw[2 * g] & 0xffff), p.aux_fmt);
+      const float m1 = f16_to_32(static_cast<uint16_t>(aw[2 * g] >> 16), p.aux_fmt);
+      const float m2 = f16_to_32(static_cast<uint16_t>(aw[2 * g + 1] & 0xffff), p.aux_fmt);
+      const float m3 = f16_to_32(static_cast<uint16_t>(aw[2 * g + 1] >> 16), p.aux_fmt);
+      x.x = fmaf(fmaf(__uint_as_float(r[4 * g + 0]), rs.ra, b.x * rs.rb), m0, x.x);
+      x.y = fmaf(fmaf(__uint_as_float(r[4 * g + 1]), rs.ra, b.y * rs.rb), m1, x.y);
+      x.z = fmaf(fmaf(__uint_as_float(r[4 * g + 2]), rs.ra, b.z * rs.rb), m2, x.z);
+      x.w = fmaf(fmaf(__uint_as_float(r[4 * g + 3]), rs.ra, b.w * rs.rb), m3, x.w);
+      *reinterpret_cast<float4*>(buf + stage_off(lane, g)) = x;
+    }
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -351,7 +374,8 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           b0 = bufp(nuse);
           mbar_wait(&abar[nuse & 1], (nuse >> 1) & 1);
           if (MODE == E_RESID_OUT32) {
-            chunk_resid(p, reinterpret_cast<const uint32_t (&)[16]>(r), col0, lane, b0, rs);
+            chunk_resid(p, reinterpret_cast<const uint32_t (&)[16]>(r), col0, lane, b0, rs,
+                        min(static_cast<long long>(row0) + lane, static_cast<long long>(p.M) - 1));
           } else {
             if (bf) chunk_math<MODE, true, false>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, b0, rs, pk);
             else    chunk_math<MODE, false, false>(p, reinterpret_cast<const uint32_t (&)[32]>(r), col0, lane, b0, rs, pk);

@@ -87,6 +87,44 @@ __global__ void small_linear_dx_kernel(const float* __restrict__ dy, long long l
   *o = accumulate ? *o + s : s;
 }
 
+// Same contraction for long N (the 768-1536-term sums of the composed-Linear un-mixing, the MPM head, the VTC sims): the
+// kernel above walks N serially in 1-3 blocks (r02g launch list: 19 launches, 1.7 ms of the step). Here a block owns
+// 128 columns k (a float4 per lane) and one slab of 64 rows n, its 8 warps take every 8th row of the slab, partial
+// sums meet in shared memory and are added to dx with one atomic per element (dx is zeroed first unless accumulating).
+__global__ void __launch_bounds__(256) small_linear_dx_split_kernel(const float* __restrict__ dy, long long lddy,
+                                                                    const float* __restrict__ yact, long long ldya,
+                                                                    const float* __restrict__ W, long long ldw,
+                                                                    float* __restrict__ dx, long long lddx, int N, int K,
+                                                                    float alpha, const float* alpha_dev, int alpha_mode) {
+  __shared__ float4 part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.y;
+  const int k = (blockIdx.x * 32 + lane) * 4;
+  const int n0 = blockIdx.z * 64, n1 = min(N, n0 + 64);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < K) {
+#pragma unroll 4
+    for (int n = n0 + warp; n < n1; n += 8) {
+      float g = dy[m * lddy + n];
+      if (yact && !(yact[m * ldya + n] > 0.f)) g = 0.f;
+      const float4 w = *reinterpret_cast<const float4*>(W + n * ldw + k);
+      acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y); acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
+    }
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && k < K) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 o = part[w][lane];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    const float a = resolve_alpha(alpha, alpha_dev, alpha_mode);
+    float* o = dx + m * lddx + k;
+    atomicAdd(o + 0, acc.x * a); atomicAdd(o + 1, acc.y * a); atomicAdd(o + 2, acc.z * a); atomicAdd(o + 3, acc.w * a);
+  }
+}
+
 // dW[n,k] (+)= alpha * sum_m dy'[m,n] x[m,k];  db[n] (+)= sum_m dy'[m,n]   (bias handled by the k == 0 thread row)
 __global__ void small_linear_dw_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ yact,
                                        long long ldya, const float* __restrict__ x, long long ldx,
@@ -440,9 +478,23 @@ extern "C" int alpro_small_linear_bwd(const float* dy, int64_t lddy, const float
   ALPRO_REQUIRE(dy && M > 0 && N > 0 && K > 0, "alpro_small_linear_bwd: bad args");
   if (dx) {
     ALPRO_REQUIRE(W, "alpro_small_linear_bwd: W needed for dx");
-    dim3 grid(static_cast<unsigned>(cdiv(K, 128)), M);
-    small_linear_dx_kernel<<<grid, 128, 0, ST>>>(dy, lddy, yact, ldya, W, ldw, dx, lddx, M, N, K, alpha, alpha_dev,
-                                                 alpha_mode, dx_accumulate);
+    const bool vec = N >= 128 && (K % 4) == 0 && (ldw % 4) == 0 && aligned16(W) && M <= 65535;
+    if (vec) {
+      if (!dx_accumulate) {
+        const cudaError_t e = cudaMemset2DAsync(dx, static_cast<size_t>(lddx) * 4, 0, static_cast<size_t>(K) * 4, M, ST);
+        if (e != cudaSuccess) {
+          set_last_error("alpro_small_linear_bwd: memset failed: %s", cudaGetErrorString(e));
+          return static_cast<int>(e);
+        }
+      }
+      dim3 grid(static_cast<unsigned>(cdiv(K, 128)), M, static_cast<unsigned>(cdiv(N, 64)));
+      small_linear_dx_split_kernel<<<grid, 256, 0, ST>>>(dy, lddy, yact, ldya, W, ldw, dx, lddx, N, K, alpha, alpha_dev,
+                                                         alpha_mode);
+    } else {
+      dim3 grid(static_cast<unsigned>(cdiv(K, 128)), M);
+      small_linear_dx_kernel<<<grid, 128, 0, ST>>>(dy, lddy, yact, ldya, W, ldw, dx, lddx, M, N, K, alpha, alpha_dev,
+                                                   alpha_mode, dx_accumulate);
+    }
     ALPRO_CHECK_LAUNCH("alpro_small_linear_bwd(dx)");
   }
   if (dW) {

@@ -303,15 +303,18 @@ def test_temporal_attention(T, N, impl, monkeypatch):
 
 
 # forward: mma.sync (default) / tcgen05 (ALPRO_ATTN_TC=1); backward: mma.sync / tcgen05 (default for 96 <= S <= 240)
-_ATTN_IMPLS = ["mma_sync", "tcgen05", "tcgen05_bwd"]
+# the tcgen05 kernels load their operand tiles by tensor-map (TMA) boxes (default) or by the per-thread cp.async gather
+# (ALPRO_ATTN_TMA=0)
+_ATTN_IMPLS = ["mma_sync", "tcgen05", "tcgen05_bwd", "tcgen05_gather", "tcgen05_bwd_gather"]
 
 
 @pytest.fixture(params=_ATTN_IMPLS)
 def attn_impl(request, monkeypatch):
-    """Sequence attention has mma.sync and tcgen05 implementations; the library reads ALPRO_ATTN_TC (forward) and
-    ALPRO_ATTN_BWD_TC (backward) on every call."""
-    monkeypatch.setenv("ALPRO_ATTN_TC", "1" if request.param == "tcgen05" else "0")
-    monkeypatch.setenv("ALPRO_ATTN_BWD_TC", "1" if request.param == "tcgen05_bwd" else "0")
+    """Sequence attention has mma.sync and tcgen05 implementations; the library reads ALPRO_ATTN_TC (forward),
+    ALPRO_ATTN_BWD_TC (backward) and ALPRO_ATTN_TMA (operand loads of the tcgen05 kernels) on every call."""
+    monkeypatch.setenv("ALPRO_ATTN_TC", "1" if request.param.startswith("tcgen05") and "bwd" not in request.param else "0")
+    monkeypatch.setenv("ALPRO_ATTN_BWD_TC", "1" if request.param.startswith("tcgen05_bwd") else "0")
+    monkeypatch.setenv("ALPRO_ATTN_TMA", "0" if request.param.endswith("gather") else "1")
     return request.param
 
 
