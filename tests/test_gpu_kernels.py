@@ -314,7 +314,7 @@ def attn_impl(request, monkeypatch):
     ALPRO_ATTN_BWD_TC (backward) and ALPRO_ATTN_TMA (operand loads of the tcgen05 kernels) on every call."""
     monkeypatch.setenv("ALPRO_ATTN_TC", "1" if request.param.startswith("tcgen05") and "bwd" not in request.param else "0")
     monkeypatch.setenv("ALPRO_ATTN_BWD_TC", "1" if request.param.startswith("tcgen05_bwd") else "0")
-    monkeypatch.setenv("ALPRO_ATTN_TMA", "0" if request.param.endswith("gather") else "1")
+    monkeypatch.setenv("ALPRO_ATTN_TMA", "0" if request.param.endswith("gather") else "1")   # 1 = also for BERT rows
     return request.param
 
 
