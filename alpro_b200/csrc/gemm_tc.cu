@@ -376,13 +376,9 @@ static bool use_tma_epilogue() {
 }
 
 // ALPRO_GEMM_2CTA=0 selects the single-CTA kernel (default: CTA-pair kernel, cta_group::2).
-static bool use_2cta() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ALPRO_GEMM_2CTA");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
+static bool use_2cta() {   // read per call (like every other switch) so that tests can run both kernels in one process
+  const char* e = getenv("ALPRO_GEMM_2CTA");
+  return !(e && e[0] == '0');
 }
 }  // namespace alpro
 

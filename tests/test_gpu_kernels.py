@@ -48,8 +48,18 @@ GEMM_CASES = [
 ]
 
 
+# The GEMM has three implementations behind one entry point: the CTA-pair kernel with the TMA-store epilogue (default,
+# gemm_tc3.cu), the CTA-pair kernel with the coalesced-store epilogue (ALPRO_GEMM_TMA_EPI=0, gemm_tc2.cu; also the
+# generic / unaligned modes of the default path) and the single-CTA kernel (ALPRO_GEMM_2CTA=0, gemm_tc.cu).
+@pytest.fixture(params=["tma_epilogue", "coalesced_epilogue", "single_cta"])
+def gemm_impl(request, monkeypatch):
+    monkeypatch.setenv("ALPRO_GEMM_TMA_EPI", "0" if request.param == "coalesced_epilogue" else "1")
+    monkeypatch.setenv("ALPRO_GEMM_2CTA", "0" if request.param == "single_cta" else "1")
+    return request.param
+
+
 @pytest.mark.parametrize("case", GEMM_CASES, ids=[f"g{i}" for i in range(len(GEMM_CASES))])
-def test_gemm16(case):
+def test_gemm16(case, gemm_impl):
     ops = _ops()
     M, N, K, al, bl, dt, ex = case
     gen = g(1)
@@ -117,9 +127,12 @@ def test_gemm16(case):
 
 
 # ------------------------------------------------------------------------------------------------------------ LN
+@pytest.mark.parametrize("ln_async", ["1", "0"])
 @pytest.mark.parametrize("d,eps,M", [(768, 1e-6, 333), (192, 1e-12, 333), (768, 1e-6, 4099), (256, 1e-6, 21000)])
-def test_layernorm_fwd_bwd(d, eps, M):
-    """M >= 4096 takes the cp.async double-buffered backward (one 12-warp block per SM), smaller M the register one."""
+def test_layernorm_fwd_bwd(d, eps, M, ln_async, monkeypatch):
+    """M >= 4096 takes the cp.async double-buffered backward (one 12-warp block per SM), smaller M — or
+    ALPRO_LN_BWD_ASYNC=0 — the register one."""
+    monkeypatch.setenv("ALPRO_LN_BWD_ASYNC", ln_async)
     ops = _ops()
     gen = g(2)
     x = torch.randn(M, d, device=DEV, generator=gen) * 2 + 0.3
@@ -380,6 +393,49 @@ def test_seq_attention_vit_layout(N, T, attn_impl):
 
 
 # ------------------------------------------------------------------------------------------------------------ heads
+@pytest.mark.parametrize("M,N,K,acc", [(1, 768, 768, False), (32, 1000, 1536, False), (5, 256, 768, True), (3, 130, 100, True)])
+def test_small_linear_dx_long_contraction(M, N, K, acc):
+    """dx = alpha * dy' W for long N: the block-split kernel (N >= 128, atomics into a zeroed / accumulated dx) with a
+    ReLU gate, strided dx rows and both accumulate modes."""
+    ops = _ops()
+    gen = g(12)
+    dy = torch.randn(M, N, device=DEV, generator=gen)
+    yact = torch.randn(M, N, device=DEV, generator=gen)
+    W = torch.randn(N, K, device=DEV, generator=gen)
+    ld = K + 12
+    dx = torch.randn(M, ld, device=DEV, generator=gen)
+    before = dx.clone()
+    ops.small_linear_bwd(dy, N, yact, None, 0, W, dx, ld, int(acc), None, None, 0, M, N, K, alpha=0.5)
+    want = 0.5 * ((dy * (yact > 0)) @ W)
+    if acc:
+        want = want + before[:, :K]
+    assert rel(dx[:, :K], want) < 1e-5
+    assert torch.equal(dx[:, K:], before[:, K:])          # the padding columns of the strided rows are untouched
+
+
+def test_cast_multi_matches_single_casts():
+    """OperandCache.refresh: one batched launch == the per-tensor casts (ragged sizes, both formats)."""
+    from alpro_b200.engine import OperandCache
+    for dt in (torch.float16, torch.bfloat16):
+        gen = g(13)
+        ps = {f"w{i}": torch.nn.Parameter(torch.randn(shape, device=DEV, generator=gen))
+              for i, shape in enumerate([(768, 768), (3, 5), (16384 * 2 + 4,), (1000, 7), (64, 192)])}
+        W = OperandCache(dt)
+        first = {n: W.get(n, p).clone() for n, p in ps.items()}
+        for n, p in ps.items():
+            assert torch.equal(first[n], p.detach().to(dt))
+        with torch.no_grad():
+            for p in ps.values():
+                v0 = p._version
+                p.data.mul_(1.5).add_(0.25)                  # .data update: the version counter does not move
+                assert p._version == v0
+        W.refresh()                                          # ONE alpro_cast_f32_to_16_multi launch
+        calls = _ops()._L.calls
+        for n, p in ps.items():
+            assert torch.equal(W.get(n, p), p.detach().to(dt)), n
+        assert _ops()._L.calls == calls                      # every get() was a hit: nothing re-cast lazily
+
+
 def test_small_linear_l2norm():
     ops = _ops()
     gen = g(10)
