@@ -151,8 +151,12 @@ class BucketedAllReduce:
     def ready(self, G, end):
         if self._G is not G:                          # new backward pass
             self._G, self._done, self.bytes = G, 0, 0
-        final = end >= G.flat.numel()
-        if end - self._done >= self.min_bucket or final:
+        n = G.flat.numel()
+        final = end >= n
+        # towards the end of the backward the buckets shrink: what is still pending when the last gradient lands is the
+        # EXPOSED part of the reduction (pull + sum + push + barrier of the tail bucket)
+        thr = self.min_bucket if end < 0.75 * n else self.min_bucket // 4
+        if end - self._done >= thr or final:
             self._reduce(G.flat, self._done, end)
             self._done = end
 

@@ -3,7 +3,12 @@
 Replaces `clip_grad_norm_(...)` + `AdamW.step()` of the reference trainers (run_video_retrieval.py:473-490,
 src/optimization/adamw.py:40-103) with two kernel launches over flat fp32 buffers. The parameters of the model are
 re-pointed to views of one flat buffer laid out exactly like the engine's GradStore, so `grad`, `exp_avg`, `exp_avg_sq`
-and the parameters are element-aligned."""
+and the parameters are element-aligned.
+
+Parameters that receive no gradient on a path (`text_encoder.cls.*` and the 400-way `visual_encoder.model.head` in
+retrieval) sit in the store with zero gradients and take the decoupled weight decay — exactly what the reference
+trainer does to them: it calls `zero_none_grad(model)` before the optimizer step (run_video_retrieval.py:443,
+src/utils/misc.py:28-31), so their `p.grad` is a zero tensor, not None, when AdamW reaches `:96-98`."""
 import torch
 
 from . import ops
