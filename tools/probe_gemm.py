@@ -38,6 +38,9 @@ CASES = {
     "perf_fc1_gelu": (50208, 3072, 768, 0, 0, "f16", "f16", {"bias": 1, "act": 1, "out16b": 1, "perf": 1}),
     "perf_dgrad": (50176, 768, 2304, 0, 1, "f16", "f16", {"perf": 1}),
     "perf_dgrad_gelugrad": (50208, 3072, 768, 0, 1, "f16", "f16", {"act": 2, "perf": 1}),
+    "perf_dgrad_sq": (50208, 768, 768, 0, 1, "f16", "f16", {"perf": 1}),          # proj / temporal_fc dgrad (B MN-major)
+    "perf_sq_kmajor": (50208, 768, 768, 0, 0, "f16", "f16", {"perf": 1}),         # same shape, B K-major
+    "perf_sq_n1536": (50208, 1536, 768, 0, 1, "f16", "f16", {"perf": 1}),
 }
 
 
