@@ -287,3 +287,27 @@ def test_unchanged_pretrain_script_builds_our_model(reference_scripts, tmp_path)
                               num_entities=cfg["num_entities"])
     with pytest.raises(RuntimeError, match="CUDA only"):
         rp.forward_step(rcfg, model, batch)
+
+
+def test_launcher_runs_a_script_against_our_classes(tmp_path):
+    """python -m alpro_b200.launch <script>: the script's reference-style imports resolve to alpro_b200 / the stand-ins."""
+    import subprocess
+    (tmp_path / "src" / "modeling").mkdir(parents=True)
+    (tmp_path / "src" / "__init__.py").write_text("")
+    (tmp_path / "src" / "modeling" / "__init__.py").write_text("")
+    script = tmp_path / "run_dummy.py"
+    script.write_text(
+        "import sys\n"
+        "import horovod.torch as hvd\n"
+        "from apex import amp\n"
+        "from src.modeling.alpro_models import AlproForPretrain, AlproForVideoTextRetrieval, Prompter\n"
+        "hvd.init()\n"
+        "assert __name__ == '__main__' and sys.argv[1:] == ['--config', 'x.json']\n"
+        "print('LAUNCH_OK', AlproForPretrain.__module__, hvd.size(), amp.initialize(1, 2, enabled=False))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, "-m", "alpro_b200.launch", str(script), "--config", "x.json"], cwd=str(tmp_path),
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "LAUNCH_OK alpro_b200.modeling 1 (1, 2)" in r.stdout, r.stdout

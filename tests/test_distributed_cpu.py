@@ -115,3 +115,58 @@ def test_vtc_data_parallel_equals_global_computation():
     for k, v in sd.items():
         ref = v.grad.numpy()
         assert abs(got[k] - ref).max() <= 1e-5 * max(1.0, abs(ref).max()), k
+
+
+def _hvd_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from alpro_b200.shims import hvd
+    hvd.init()                                     # joins the group from the torchrun-style environment (gloo: no CUDA)
+    ok = (hvd.rank(), hvd.size(), hvd.local_rank()) == (rank, world, rank)
+    # allgather: ragged first dimension, rank order (src/utils/distributed.py:234-235 gathers sizes then payloads)
+    x = torch.full((rank + 2, 3), float(rank))
+    g = hvd.allgather(x)
+    ok = ok and g.shape == (sum(r + 2 for r in range(world)), 3) and float(g[0, 0]) == 0.0 and float(g[-1, 0]) == world - 1
+    # its gradient: sum over ranks, local slice (Horovod 0.19.4 allgather backward)
+    y = torch.ones(2, 4, requires_grad=True)
+    (hvd.allgather(y) * (rank + 1)).sum().backward()
+    ok = ok and torch.allclose(y.grad, torch.full((2, 4), float(sum(r + 1 for r in range(world)))))
+    t = torch.arange(5.0) * (rank + 1)
+    hvd.allreduce_(t)                              # average
+    ok = ok and torch.allclose(t, torch.arange(5.0) * (sum(r + 1 for r in range(world)) / world))
+    b = torch.full((3,), float(rank))
+    hvd.broadcast_(b, root_rank=1)
+    ok = ok and float(b[0]) == 1.0
+    # DistributedOptimizer: gradients averaged by synchronize(), parameters broadcast from rank 0
+    torch.manual_seed(rank)
+    lin = torch.nn.Linear(4, 2)
+    hvd.broadcast_parameters(lin.state_dict(), root_rank=0)
+    opt = hvd.DistributedOptimizer(torch.optim.SGD(lin.parameters(), lr=1.0), named_parameters=lin.named_parameters())
+    hvd.broadcast_optimizer_state(opt, root_rank=0)
+    w0 = lin.weight.detach().clone()
+    lin(torch.full((1, 4), float(rank + 1))).sum().backward()
+    opt.synchronize()
+    want = torch.full((2, 4), sum(r + 1 for r in range(world)) / world)
+    ok = ok and torch.allclose(lin.weight.grad, want)
+    with opt.skip_synchronize():
+        opt.step()
+    ok = ok and torch.allclose(lin.weight.detach(), w0 - want)
+    q.put((rank, bool(ok), lin.weight.detach().numpy().copy()))
+    dist.barrier()
+    hvd.shutdown()
+
+
+def test_horovod_stand_in_world_size_2():
+    """alpro_b200.shims.hvd over gloo: the collective semantics the unchanged run scripts rely on."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hvd_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {r: (ok, w) for r, ok, w in (q.get(timeout=120) for _ in range(world))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][0] and got[1][0]
+    assert (got[0][1] == got[1][1]).all()          # same start (broadcast) + same averaged gradient = same weights
