@@ -324,7 +324,7 @@ def run_ours(args):
     chk_loss.backward()
     gflat = model.engine.last_grads.flat
     finite = bool(torch.isfinite(chk_loss).item()) and bool(torch.isfinite(gflat).all().item())
-    loss_vals = {k: round(float(v), 5) for k, v in chk.items() if k.endswith("_loss") and v is not None}
+    loss_vals = {k: round(float(v.detach()), 5) for k, v in chk.items() if k.endswith("_loss") and v is not None}
     gnorm = float(gflat.double().norm())
     if world > 1:
         acomm.allreduce_gradients(model)
