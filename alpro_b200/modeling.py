@@ -237,6 +237,8 @@ class AlproBaseModel(nn.Module):
                                   num_entities=self._cfg.get("num_entities"))
         self.engine.sampler, self.engine.comm = old.sampler, old.comm
         self.engine.grad_ready_hook = old.grad_ready_hook
+        self.engine.grad_alloc = getattr(old, "grad_alloc", None)      # data-parallel hooks survive the switch
+        self.engine.neg_seed = old.neg_seed
         return self
 
     # ---- plumbing

@@ -24,7 +24,7 @@ def run(device, world, rank):
     (out["itc_loss"] + out["itm_loss"]).backward()
     comm.allreduce_gradients(model)
     torch.cuda.synchronize()
-    mine = dict(itc=float(out["itc_loss"]), itm=float(out["itm_loss"]),
+    mine = dict(itc=float(out["itc_loss"].detach()), itm=float(out["itm_loss"].detach()),
                 neg=out["_neg_video"].tolist() + out["_neg_text"].tolist())
     got = [None] * world
     dist.all_gather_object(got, mine)
