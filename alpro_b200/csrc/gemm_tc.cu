@@ -414,6 +414,23 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
     const int units = pair ? num_sms() / 2 : num_sms();
     if (tiles < units) split = (2 * units) / tiles;
     if (split > p.num_k_blocks / 4) split = p.num_k_blocks / 4;
+    // ALPRO_GEMM_SPLITK=model: pick the split that minimises waves * (k-blocks per item + epilogue), the epilogue of a
+    // split-K item (TMA reduce-add of a 128x256 fp32 tile per CTA) costed as `epi` k-blocks (experiment, r02)
+    static const char* sk_env = getenv("ALPRO_GEMM_SPLITK");
+    if (sk_env && sk_env[0] == 'm' && tiles < 4 * units) {
+      const int epi = sk_env[5] ? atoi(sk_env + 5) : 8;   // "model" or "model<epi>"
+      long best = -1;
+      int best_s = 1;
+      const int smax = p.num_k_blocks / 4 > 0 ? p.num_k_blocks / 4 : 1;
+      for (int sct = 1; sct <= smax && sct <= 64; ++sct) {
+        const long kb = cdiv(p.num_k_blocks, sct);
+        const long items = static_cast<long>(tiles) * cdiv(p.num_k_blocks, kb);
+        const long waves = cdiv(items, units);
+        const long cost = waves * (kb + (sct > 1 ? epi : 2));
+        if (best < 0 || cost < best) { best = cost; best_s = sct; }
+      }
+      split = best_s;
+    }
   }
   if (split < 1) split = 1;
   if (split > p.num_k_blocks) split = p.num_k_blocks;
