@@ -414,11 +414,13 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
     const int units = pair ? num_sms() / 2 : num_sms();
     if (tiles < units) split = (2 * units) / tiles;
     if (split > p.num_k_blocks / 4) split = p.num_k_blocks / 4;
-    // ALPRO_GEMM_SPLITK=model: pick the split that minimises waves * (k-blocks per item + epilogue), the epilogue of a
-    // split-K item (TMA reduce-add of a 128x256 fp32 tile per CTA) costed as `epi` k-blocks (experiment, r02)
+    // Default since r02 (tools/probe_gemm.py, isolated launches: 768x768x50208 1037 -> 1217 TFLOP/s, 768x3072x50208
+    // 1270 -> 1431, 2304x768x50176 unchanged): pick the split that minimises waves * (k-blocks per item + epilogue),
+    // the epilogue of a split-K item (TMA reduce-add of a 128x256 fp32 tile per CTA) costed as 8 k-blocks. The rule
+    // above filled two waves regardless of how unevenly. ALPRO_GEMM_SPLITK=two_waves restores it (read once).
     static const char* sk_env = getenv("ALPRO_GEMM_SPLITK");
-    if (sk_env && sk_env[0] == 'm' && tiles < 4 * units) {
-      const int epi = sk_env[5] ? atoi(sk_env + 5) : 8;   // "model" or "model<epi>"
+    if (!(sk_env && sk_env[0] == 't') && tiles < 4 * units) {
+      const int epi = 8;
       long best = -1;
       int best_s = 1;
       const int smax = p.num_k_blocks / 4 > 0 ? p.num_k_blocks / 4 : 1;
