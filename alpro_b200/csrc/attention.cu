@@ -192,6 +192,7 @@ __device__ __forceinline__ void tattn_row_probs_reg(const float (&q)[DPP], const
 // grid: ceil(B*N*heads / warps_per_block); each warp = one (b, n, head). cls rows are zero-filled by the n==0 warps.
 template <int T, bool BF>
 __global__ void __launch_bounds__(128, 3) tattn_fwd_kernel(const TAttnParams p) {
+  pdl_grid_sync();
   constexpr int PARTS = 32 / T, DPP = DH / PARTS;
   const int lane = threadIdx.x & 31;
   const long long unit = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(128, 3) tattn_fwd_kernel(const TAttnParams p) 
 
 template <int T, bool BF>
 __global__ void __launch_bounds__(128, 4) tattn_bwd_kernel(const TAttnParams p) {
+  pdl_grid_sync();
   constexpr int PARTS = 32 / T, DPP = DH / PARTS, WPB = 4;
   __shared__ __align__(16) float sQ[WPB][T][DH], sK[WPB][T][DH], sV[WPB][T][DH], sG[WPB][T][DH];
   __shared__ float sP[WPB][T][T], sDS[WPB][T][T];
@@ -426,6 +428,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // otherwise NT is an upper bound and the loops are predicated on the runtime count.
 template <bool BF, int NT, bool EXACT>
 __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) uint8_t sm[];
   const int head = blockIdx.x, seq = blockIdx.y;
   const SeqRows rows = make_rows(p, seq);
@@ -563,6 +566,7 @@ __global__ void __launch_bounds__(128) sattn_fwd_kernel(const SAttnParams p) {
 // Phase A: each warp owns 16-query tiles -> dQ.   Phase B: each warp owns 16-key tiles -> dK, dV (recomputing S^T).
 template <bool BF>
 __global__ void __launch_bounds__(256, 2) sattn_bwd_kernel(const SAttnParams p) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) uint8_t sm[];
   const int head = blockIdx.x, seq = blockIdx.y;
   const SeqRows rows = make_rows(p, seq);
@@ -882,6 +886,7 @@ __global__ void __launch_bounds__(256, 2) sattn_fwd_tc_kernel(const __grid_const
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  pdl_grid_sync();   // setup above overlapped the previous kernel's tail (common.h)
   // thread t owns the 16-byte chunk ch = t & 7 of rows (t >> 3) + 32 u of every tile
   const int ch = tid & 7, r0 = tid >> 3;
   const uint32_t swz = static_cast<uint32_t>((ch ^ (r0 & 7)) << 4);   // (row & 7) == (r0 & 7): rows advance by 32
@@ -1227,6 +1232,7 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const __grid_const
       }
     }
   }
+  pdl_grid_sync();   // barrier setup above overlapped the previous kernel's tail (common.h)
 
   if (warp == 8) {
     if (lane == 0) {
@@ -1594,6 +1600,7 @@ __global__ void __launch_bounds__(288, 1) sattn_bwd_tc_kernel(const __grid_const
 // dqkv[group cls row] = sum over the group's seq_div frames of the per-sequence cls-row gradients
 __global__ void cls_qkv_reduce_kernel(const float* __restrict__ part, uint16_t* __restrict__ dqkv, long long ld,
                                       long long clip_rows, int groups, int seq_div, int d3, int fmt) {
+  pdl_grid_sync();
   const long long total = static_cast<long long>(groups) * d3;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1655,20 +1662,20 @@ extern "C" int alpro_temporal_attn_fwd(const void* qkv, int64_t ld_qkv, void* ou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (T) {
     case 1:
-      if (fmt) tattn_fwd_kernel<1, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_fwd_kernel<1, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_fwd_kernel<1, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_fwd_kernel<1, false>, grid, wpb * 32, 0, st, p);
       break;
     case 2:
-      if (fmt) tattn_fwd_kernel<2, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_fwd_kernel<2, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_fwd_kernel<2, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_fwd_kernel<2, false>, grid, wpb * 32, 0, st, p);
       break;
     case 4:
-      if (fmt) tattn_fwd_kernel<4, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_fwd_kernel<4, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_fwd_kernel<4, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_fwd_kernel<4, false>, grid, wpb * 32, 0, st, p);
       break;
     case 8:
-      if (fmt) tattn_fwd_kernel<8, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_fwd_kernel<8, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_fwd_kernel<8, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_fwd_kernel<8, false>, grid, wpb * 32, 0, st, p);
       break;
     default: set_last_error("alpro_temporal_attn_fwd: T=%d unsupported (1,2,4,8)", T); return ALPRO_ENOTSUP;
   }
@@ -1696,20 +1703,20 @@ extern "C" int alpro_temporal_attn_bwd(const void* qkv, int64_t ld_qkv, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (T) {
     case 1:
-      if (fmt) tattn_bwd_kernel<1, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_bwd_kernel<1, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_bwd_kernel<1, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_bwd_kernel<1, false>, grid, wpb * 32, 0, st, p);
       break;
     case 2:
-      if (fmt) tattn_bwd_kernel<2, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_bwd_kernel<2, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_bwd_kernel<2, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_bwd_kernel<2, false>, grid, wpb * 32, 0, st, p);
       break;
     case 4:
-      if (fmt) tattn_bwd_kernel<4, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_bwd_kernel<4, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_bwd_kernel<4, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_bwd_kernel<4, false>, grid, wpb * 32, 0, st, p);
       break;
     case 8:
-      if (fmt) tattn_bwd_kernel<8, true><<<grid, wpb * 32, 0, st>>>(p);
-      else tattn_bwd_kernel<8, false><<<grid, wpb * 32, 0, st>>>(p);
+      if (fmt) launch_k(tattn_bwd_kernel<8, true>, grid, wpb * 32, 0, st, p);
+      else launch_k(tattn_bwd_kernel<8, false>, grid, wpb * 32, 0, st, p);
       break;
     default: set_last_error("alpro_temporal_attn_bwd: T=%d unsupported (1,2,4,8)", T); return ALPRO_ENOTSUP;
   }
@@ -1856,11 +1863,11 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
     if (tma) {                                                                                      \
       rc = set_smem(sattn_fwd_tc_kernel<BF, DR, MK, true>, smem_tc);                                \
       if (rc) return rc;                                                                            \
-      sattn_fwd_tc_kernel<BF, DR, MK, true><<<grid, 256, smem_tc, st>>>(tmAll, tmQ0, tmQ1, p);      \
+      launch_k(sattn_fwd_tc_kernel<BF, DR, MK, true>, grid, 256, smem_tc, st, tmAll, tmQ0, tmQ1, p);      \
     } else {                                                                                        \
       rc = set_smem(sattn_fwd_tc_kernel<BF, DR, MK, false>, smem_tc);                               \
       if (rc) return rc;                                                                            \
-      sattn_fwd_tc_kernel<BF, DR, MK, false><<<grid, 256, smem_tc, st>>>(tmAll, tmQ0, tmQ1, p);     \
+      launch_k(sattn_fwd_tc_kernel<BF, DR, MK, false>, grid, 256, smem_tc, st, tmAll, tmQ0, tmQ1, p);     \
     }                                                                                               \
   } while (0)
 #define LAUNCH_FWD_TC_F(BF)                                                          \
@@ -1879,7 +1886,7 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
   do {                                                                       \
     rc = set_smem(sattn_fwd_kernel<BF, NT, EX>, smem);                       \
     if (rc) return rc;                                                       \
-    sattn_fwd_kernel<BF, NT, EX><<<grid, 128, smem, st>>>(p);                \
+    launch_k(sattn_fwd_kernel<BF, NT, EX>, grid, 128, smem, st, p);                \
   } while (0)
 #define LAUNCH_FWD_T(BF)                                                                              \
   do {                                                                                                \
@@ -1952,11 +1959,11 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
     if (tma) {                                                                            \
       rc = set_smem(sattn_bwd_tc_kernel<BF, DR, true>, smem_tc);                          \
       if (rc) return rc;                                                                  \
-      sattn_bwd_tc_kernel<BF, DR, true><<<grid, 288, smem_tc, st>>>(tmQKV, tmDO, p);      \
+      launch_k(sattn_bwd_tc_kernel<BF, DR, true>, grid, 288, smem_tc, st, tmQKV, tmDO, p);      \
     } else {                                                                              \
       rc = set_smem(sattn_bwd_tc_kernel<BF, DR, false>, smem_tc);                         \
       if (rc) return rc;                                                                  \
-      sattn_bwd_tc_kernel<BF, DR, false><<<grid, 288, smem_tc, st>>>(tmQKV, tmDO, p);     \
+      launch_k(sattn_bwd_tc_kernel<BF, DR, false>, grid, 288, smem_tc, st, tmQKV, tmDO, p);     \
     }                                                                                     \
   } while (0)
     if (fmt == 1) {
@@ -1969,18 +1976,18 @@ extern "C" int alpro_seq_attn_bwd(const void* qkv, int64_t ld_qkv, const float* 
   } else if (fmt == 1) {
     rc = set_smem(sattn_bwd_kernel<true>, smem);
     if (rc) return rc;
-    sattn_bwd_kernel<true><<<grid, 256, smem, st>>>(p);
+    launch_k(sattn_bwd_kernel<true>, grid, 256, smem, st, p);
   } else {
     rc = set_smem(sattn_bwd_kernel<false>, smem);
     if (rc) return rc;
-    sattn_bwd_kernel<false><<<grid, 256, smem, st>>>(p);
+    launch_k(sattn_bwd_kernel<false>, grid, 256, smem, st, p);
   }
   ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd");
   if (seq_div > 1) {
     const int groups = nseq / seq_div;
     const long long total = static_cast<long long>(groups) * 3 * p.d;
     long long g = cdiv(total, 256);
-    cls_qkv_reduce_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(dcls_qkv_scratch, p.dqkv, ld_qkv, clip_rows, groups,
+    launch_k(cls_qkv_reduce_kernel, static_cast<unsigned>(g), 256, 0, st, dcls_qkv_scratch, p.dqkv, ld_qkv, clip_rows, groups,
                                                                     seq_div, 3 * p.d, fmt);
     ALPRO_CHECK_LAUNCH("alpro_seq_attn_bwd(cls reduce)");
   }
@@ -1991,6 +1998,7 @@ namespace alpro {
 namespace {
 __global__ void attn_drop_mask_kernel(float* __restrict__ out, int S, int S_pad, int nseq, int heads, uint32_t thr,
                                       uint32_t seed, float scale) {
+  pdl_grid_sync();
   SAttnParams p{};
   p.heads = heads; p.drop_thr = thr; p.drop_seed = seed; p.drop_scale = scale;
   const long long total = static_cast<long long>(nseq) * heads * S * S;
@@ -2011,7 +2019,7 @@ extern "C" int alpro_attn_dropout_mask(float* out, int S, int nseq, int heads, f
                                        void* stream) {
   ALPRO_REQUIRE(out && S > 0 && nseq > 0 && heads > 0 && drop_p > 0.f && drop_p < 1.f, "alpro_attn_dropout_mask: bad args");
   const int S_pad = (S + 15) & ~15;
-  attn_drop_mask_kernel<<<num_sms() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(attn_drop_mask_kernel, num_sms() * 8, 256, 0, static_cast<cudaStream_t>(stream), 
       out, S, S_pad, nseq, heads, drop_threshold(drop_p), drop_seed, 1.0f / (1.0f - drop_p));
   ALPRO_CHECK_LAUNCH("alpro_attn_dropout_mask");
   return 0;

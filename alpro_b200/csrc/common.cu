@@ -1,5 +1,6 @@
 // Library-wide host utilities: last-error string, device properties.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -27,6 +28,11 @@ int num_sms() {
       n = 148;  // B200
   });
   return n;
+}
+
+bool pdl_enabled() {   // read per launch (~50 ns) so that a test or the bench can switch it inside one process
+  const char* e = getenv("ALPRO_PDL");
+  return !(e && e[0] == '0');
 }
 
 }  // namespace alpro

@@ -17,6 +17,7 @@ __device__ __forceinline__ float load_any(const void* p, int kind, long long idx
 
 // ------------------------------------------------------------------------------------------------ cast
 __global__ void cast_f32_to_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n, int fmt) {
+  pdl_grid_sync();
   long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (; i + 3 < n; i += stride) {
@@ -36,6 +37,7 @@ __global__ void cast_f32_to_16_kernel(const float* __restrict__ src, uint16_t* _
 // one block per chunk, so ~200 per-tensor launches become one.
 constexpr int CAST_CHUNK = 16384;
 __global__ void __launch_bounds__(256) cast_multi_kernel(const long long* __restrict__ table, int fmt) {
+  pdl_grid_sync();
   const long long* e = table + 3LL * blockIdx.x;
   const float* __restrict__ src = reinterpret_cast<const float*>(e[0]);
   uint16_t* __restrict__ dst = reinterpret_cast<uint16_t*>(e[1]);
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(256) cast_multi_kernel(const long long* __rest
 // out[i] = keep_i / (1 - p) with keep_i ~ Bernoulli(1 - p) from the counter hash (nn.Dropout, xbert.py:178,331,358,436)
 __global__ void dropout_mask_kernel(uint16_t* __restrict__ out, int fmt, long long n, uint32_t thr, float scale,
                                     uint32_t seed) {
+  pdl_grid_sync();
   const long long pairs = (n + 1) >> 1;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -73,6 +76,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long ldx,
                                      long long ld16, int fmt, float* __restrict__ mean_out,
                                      float* __restrict__ rstd_out, const uint16_t* __restrict__ mul16,
                                      long long ldmul) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(192, 3) layernorm_bwd_kernel(const void* __res
                                      const uint16_t* __restrict__ dx16_mul16, long long lddxmul,
                                      const float* __restrict__ dx16_row_scale,
                                      const float* __restrict__ colsum_row_scale) {
+  pdl_grid_sync();
   // Per-warp accumulators for dgamma / dbeta / bias column sums live in shared memory ([warp][3][d], each lane owns its
   // float4 slots -> conflict-free, no atomics) so that registers stay free for more resident warps.
   extern __shared__ float red[];
@@ -303,6 +308,7 @@ layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long l
                            float* __restrict__ colsum, int colsum_zero_period, const uint16_t* __restrict__ dy_mul16,
                            long long lddymul, const uint16_t* __restrict__ dx16_mul16, long long lddxmul,
                            const float* __restrict__ dx16_row_scale, const float* __restrict__ colsum_row_scale) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t lnb_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -483,6 +489,7 @@ layernorm_bwd_async_kernel(const void* __restrict__ dy, int dy_kind, long long l
 __global__ void __launch_bounds__(256) colsum16_kernel(const uint16_t* __restrict__ x, int fmt, long long ld,
                                                        long long M, int N, float* __restrict__ out, float alpha,
                                                        int zero_period) {
+  pdl_grid_sync();
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -537,6 +544,7 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const uint16_t* __restric
 
 __global__ void colsum32_kernel(const float* __restrict__ x, long long ld, long long M, int N, float* __restrict__ out,
                                 float alpha) {
+  pdl_grid_sync();
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= N) return;
   float s = 0.f;
@@ -550,6 +558,7 @@ __global__ void colsum32_kernel(const float* __restrict__ x, long long ld, long 
 // c*P*P + ky*P + kx matches Conv2d weight [d,3,P,P].view(d,-1) (PatchEmbed, vit.py:230-238).
 __global__ void patchify_kernel(const float* __restrict__ frames, uint16_t* __restrict__ out, int fmt, int B, int T,
                                 int H, int W, int P) {
+  pdl_grid_sync();
   const int gw = W / P, gh = H / P;
   const int N = gw * gh;
   const int Kd = 3 * P * P;
@@ -583,6 +592,7 @@ __global__ void patchify_kernel(const float* __restrict__ frames, uint16_t* __re
 __global__ void patchify_u8_kernel(const uint8_t* __restrict__ frames, uint16_t* __restrict__ out, int fmt, int B,
                                    int T, int H, int W, int P, float s0, float s1, float s2, float o0, float o1,
                                    float o2) {
+  pdl_grid_sync();
   const int gw = W / P, gh = H / P;
   const int N = gw * gh;
   const int Kd = 3 * P * P;
@@ -616,6 +626,7 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ frames, uint16_t*
 __global__ void vit_embed_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ cls,
                                      const float* __restrict__ pos, const float* __restrict__ tim,
                                      float* __restrict__ x, int B, int N, int T, int d) {
+  pdl_grid_sync();
   const int d4 = d >> 2;
   const long long total = static_cast<long long>(B) * (1 + N * T) * d4;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -644,6 +655,7 @@ __global__ void vit_embed_fwd_kernel(const float* __restrict__ proj, const float
 // (outputs zero-initialised by the caller); threads over d.
 __global__ void vit_embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls, float* __restrict__ dpos,
                                      float* __restrict__ dtim, int B, int N, int T, int d, float alpha) {
+  pdl_grid_sync();
   const int which = blockIdx.x;
   const int b = blockIdx.y;
   const long long S = 1 + static_cast<long long>(N) * T;
@@ -669,6 +681,7 @@ __global__ void vit_embed_bwd_kernel(const float* __restrict__ dx, float* __rest
 // video_embeds[b,0] = xn[b,0]; video_embeds[b,1+n] = mean_t xn[b,1+n*T+t]     (TimeSformer.forward_features :484-492)
 __global__ void temporal_pool_fwd_kernel(const float* __restrict__ xn, float* __restrict__ out, int B, int N, int T,
                                          int d) {
+  pdl_grid_sync();
   const int d4 = d >> 2;
   const long long total = static_cast<long long>(B) * (1 + N) * d4;
   const float inv = 1.f / T;
@@ -696,6 +709,7 @@ __global__ void temporal_pool_fwd_kernel(const float* __restrict__ xn, float* __
 
 __global__ void temporal_pool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dxn, int B, int N, int T,
                                          int d, float alpha) {
+  pdl_grid_sync();
   const int d4 = d >> 2;
   const long long total = static_cast<long long>(B) * (1 + N * T) * d4;
   const float inv = alpha / T;
@@ -717,6 +731,7 @@ __global__ void temporal_pool_bwd_kernel(const float* __restrict__ dout, float* 
 __global__ void bert_embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
                                          const float* __restrict__ pos, const float* __restrict__ type,
                                          float* __restrict__ out, long long BL, int L, int h) {
+  pdl_grid_sync();
   const int h4 = h >> 2;
   const long long total = BL * h4;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -734,6 +749,7 @@ __global__ void bert_embed_gather_kernel(const long long* __restrict__ ids, cons
 __global__ void bert_embed_scatter_kernel(const long long* __restrict__ ids, const float* __restrict__ de,
                                           float* __restrict__ dword, float* __restrict__ dpos,
                                           float* __restrict__ dtype, long long BL, int L, int h, float alpha) {
+  pdl_grid_sync();
   const long long total = BL * h;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -756,6 +772,7 @@ __global__ void fusion_gather_fwd_kernel(const float* __restrict__ text, const f
                                          const int* __restrict__ vi, float* __restrict__ out32,
                                          uint16_t* __restrict__ out16, int fmt, float* __restrict__ add_mask, int S,
                                          int L, int Nv, int h) {
+  pdl_grid_sync();
   const int h4 = h >> 2;
   const int R = L + Nv;
   const long long total = static_cast<long long>(S) * R * h4;
@@ -786,6 +803,7 @@ __global__ void fusion_gather_fwd_kernel(const float* __restrict__ text, const f
 __global__ void fusion_gather_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ ti,
                                          const int* __restrict__ vi, float* __restrict__ dtext,
                                          float* __restrict__ dvideo, int S, int L, int Nv, int h) {
+  pdl_grid_sync();
   const int R = L + Nv;
   const long long total = static_cast<long long>(S) * R * h;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -804,6 +822,7 @@ __global__ void fusion_gather_bwd_kernel(const float* __restrict__ dout, const i
 // of the linear `proj`, with which the mean commutes).
 __global__ void cls_mean_fwd_kernel(const uint16_t* __restrict__ cls_t, uint16_t* __restrict__ o, long long ldo,
                                     int fmt, int B, int T, int S, int d, const float* __restrict__ wgt) {
+  pdl_grid_sync();
   // cls_t: [B, T, d]; o row b*S gets the mean
   const long long total = static_cast<long long>(B) * d;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -834,7 +853,7 @@ extern "C" int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int 
   ALPRO_REQUIRE(src && dst && n >= 0, "alpro_cast_f32_to_16: bad args");
   if (n == 0) return 0;
   ALPRO_REQUIRE(aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "alpro_cast_f32_to_16: alignment");
-  cast_f32_to_16_kernel<<<grid_for(cdiv(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cast_f32_to_16_kernel, grid_for(cdiv(n, 4), 256), 256, 0, static_cast<cudaStream_t>(stream), 
       src, static_cast<uint16_t*>(dst), n, fmt);
   ALPRO_CHECK_LAUNCH("alpro_cast_f32_to_16");
   return 0;
@@ -842,7 +861,7 @@ extern "C" int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int 
 
 extern "C" int alpro_cast_f32_to_16_multi(const int64_t* table, int num_chunks, int fmt, void* stream) {
   ALPRO_REQUIRE(table && num_chunks > 0, "alpro_cast_f32_to_16_multi: bad args");
-  cast_multi_kernel<<<static_cast<unsigned>(num_chunks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cast_multi_kernel, static_cast<unsigned>(num_chunks), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(table), fmt);
   ALPRO_CHECK_LAUNCH("alpro_cast_f32_to_16_multi");
   return 0;
@@ -856,7 +875,7 @@ extern "C" int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gam
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_fwd: d=%d unsupported (multiple of 4, <= 1024)", d);
   ALPRO_REQUIRE(ldx % 4 == 0 && (!out32 || ld32 % 4 == 0) && (!out16 || ld16 % 4 == 0), "alpro_layernorm_fwd: ld");
   const int wpb = 8;
-  layernorm_fwd_kernel<<<static_cast<unsigned>(cdiv(M, wpb)), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(layernorm_fwd_kernel, static_cast<unsigned>(cdiv(M, wpb)), wpb * 32, 0, static_cast<cudaStream_t>(stream), 
       x, ldx, gamma, beta, eps, M, d, out32, ld32, static_cast<uint16_t*>(out16), ld16, out16_fmt, mean, rstd,
       static_cast<const uint16_t*>(mul16), ldmul);
   ALPRO_CHECK_LAUNCH("alpro_layernorm_fwd");
@@ -890,7 +909,7 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
   do {                                                                                                                 \
     cudaFuncSetAttribute(layernorm_bwd_async_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
                          static_cast<int>(smem_a));                                                                    \
-    layernorm_bwd_async_kernel<NV><<<grid_a, LNB_WARPS * 32, smem_a, st>>>(                                            \
+    launch_k(layernorm_bwd_async_kernel<NV>, grid_a, LNB_WARPS * 32, smem_a, st,                                             \
         dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, accumulate, static_cast<uint16_t*>(dx16),      \
         lddx16, dx16_fmt, zero_period, dgamma, dbeta, param_scale, colsum, colsum_zero_period,                         \
         static_cast<const uint16_t*>(dy_mul16), lddymul, static_cast<const uint16_t*>(dx16_mul16), lddxmul,            \
@@ -913,7 +932,7 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
   cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));  \
   cudaFuncSetAttribute(layernorm_bwd_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout,                      \
                        cudaSharedmemCarveoutMaxShared);                                                                \
-  layernorm_bwd_kernel<NV><<<grid, wpb * 32, smem, st>>>(dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, \
+  launch_k(layernorm_bwd_kernel<NV>, grid, wpb * 32, smem, st, dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, \
                                                          accumulate, static_cast<uint16_t*>(dx16), lddx16, dx16_fmt,   \
                                                          zero_period, dgamma, dbeta, param_scale, colsum,              \
                                                          colsum_zero_period, static_cast<const uint16_t*>(dy_mul16),   \
@@ -934,7 +953,7 @@ extern "C" int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int 
   int rows = static_cast<int>(M < 512 ? M : 512);
   if (kind == 0) {
     dim3 grid(static_cast<unsigned>(cdiv(N, 128)), rows);
-    colsum32_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ld, M, N, out,
+    launch_k(colsum32_kernel, grid, 128, 0, static_cast<cudaStream_t>(stream), static_cast<const float*>(x), ld, M, N, out,
                                                                           alpha);
   } else {
     int gy = static_cast<int>(cdiv(M, 8 * 16));   // >= 16 rows per warp
@@ -942,7 +961,7 @@ extern "C" int alpro_colsum(const void* x, int kind, int64_t ld, int64_t M, int 
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
     dim3 grid(static_cast<unsigned>(cdiv(N, 256)), gy);
-    colsum16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(x), kind - 1, ld,
+    launch_k(colsum16_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(x), kind - 1, ld,
                                                                           M, N, out, alpha, zero_period);
   }
   ALPRO_CHECK_LAUNCH("alpro_colsum");
@@ -954,7 +973,7 @@ extern "C" int alpro_patchify(const float* frames, void* out16, int fmt, int B, 
   ALPRO_REQUIRE(frames && out16 && B > 0 && T > 0, "alpro_patchify: bad args");
   ALPRO_REQUIRE(P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "alpro_patchify: P=%d H=%d W=%d unsupported", P, H, W);
   const long long total = static_cast<long long>(B) * (1 + (H / P) * (W / P) * T) * (3 * P * P / 4);
-  patchify_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(patchify_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       frames, static_cast<uint16_t*>(out16), fmt, B, T, H, W, P);
   ALPRO_CHECK_LAUNCH("alpro_patchify");
   return 0;
@@ -964,7 +983,7 @@ extern "C" int alpro_vit_embed_fwd(const float* proj, const float* cls, const fl
                                    int B, int N, int T, int d, void* stream) {
   ALPRO_REQUIRE(proj && cls && pos && tim && x && d % 4 == 0, "alpro_vit_embed_fwd: bad args");
   const long long total = static_cast<long long>(B) * (1 + N * T) * (d / 4);
-  vit_embed_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(proj, cls, pos, tim, x, B,
+  launch_k(vit_embed_fwd_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), proj, cls, pos, tim, x, B,
                                                                                            N, T, d);
   ALPRO_CHECK_LAUNCH("alpro_vit_embed_fwd");
   return 0;
@@ -973,7 +992,7 @@ extern "C" int alpro_vit_embed_fwd(const float* proj, const float* cls, const fl
 extern "C" int alpro_vit_embed_bwd(const float* dx, float* dcls, float* dpos, float* dtim, int B, int N, int T, int d,
                                    float alpha, void* stream) {
   ALPRO_REQUIRE(dx && dcls && dpos && dtim, "alpro_vit_embed_bwd: bad args");
-  vit_embed_bwd_kernel<<<dim3(1 + N + T, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, dcls, dpos, dtim, B, N,
+  launch_k(vit_embed_bwd_kernel, dim3(1 + N + T, B), 256, 0, static_cast<cudaStream_t>(stream), dx, dcls, dpos, dtim, B, N,
                                                                                           T, d, alpha);
   ALPRO_CHECK_LAUNCH("alpro_vit_embed_bwd");
   return 0;
@@ -982,7 +1001,7 @@ extern "C" int alpro_vit_embed_bwd(const float* dx, float* dcls, float* dpos, fl
 extern "C" int alpro_temporal_pool_fwd(const float* xn, float* out, int B, int N, int T, int d, void* stream) {
   ALPRO_REQUIRE(xn && out && d % 4 == 0, "alpro_temporal_pool_fwd: bad args");
   const long long total = static_cast<long long>(B) * (1 + N) * (d / 4);
-  temporal_pool_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xn, out, B, N, T, d);
+  launch_k(temporal_pool_fwd_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), xn, out, B, N, T, d);
   ALPRO_CHECK_LAUNCH("alpro_temporal_pool_fwd");
   return 0;
 }
@@ -991,7 +1010,7 @@ extern "C" int alpro_temporal_pool_bwd(const float* dout, float* dxn, int B, int
                                        void* stream) {
   ALPRO_REQUIRE(dout && dxn && d % 4 == 0, "alpro_temporal_pool_bwd: bad args");
   const long long total = static_cast<long long>(B) * (1 + N * T) * (d / 4);
-  temporal_pool_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, dxn, B, N, T, d,
+  launch_k(temporal_pool_bwd_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), dout, dxn, B, N, T, d,
                                                                                                alpha);
   ALPRO_CHECK_LAUNCH("alpro_temporal_pool_bwd");
   return 0;
@@ -1000,7 +1019,7 @@ extern "C" int alpro_temporal_pool_bwd(const float* dout, float* dxn, int B, int
 extern "C" int alpro_bert_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type,
                                        float* out, int64_t BL, int L, int h, void* stream) {
   ALPRO_REQUIRE(ids && word && pos && type && out && h % 4 == 0, "alpro_bert_embed_gather: bad args");
-  bert_embed_gather_kernel<<<grid_for(BL * (h / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bert_embed_gather_kernel, grid_for(BL * (h / 4), 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(ids), word, pos, type, out, BL, L, h);
   ALPRO_CHECK_LAUNCH("alpro_bert_embed_gather");
   return 0;
@@ -1009,7 +1028,7 @@ extern "C" int alpro_bert_embed_gather(const int64_t* ids, const float* word, co
 extern "C" int alpro_bert_embed_scatter(const int64_t* ids, const float* de, float* dword, float* dpos, float* dtype,
                                         int64_t BL, int L, int h, float alpha, void* stream) {
   ALPRO_REQUIRE(ids && de && dword && dpos && dtype, "alpro_bert_embed_scatter: bad args");
-  bert_embed_scatter_kernel<<<grid_for(BL * h, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(bert_embed_scatter_kernel, grid_for(BL * h, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(ids), de, dword, dpos, dtype, BL, L, h, alpha);
   ALPRO_CHECK_LAUNCH("alpro_bert_embed_scatter");
   return 0;
@@ -1020,7 +1039,7 @@ extern "C" int alpro_fusion_gather_fwd(const float* text, const float* video, co
                                        int L, int Nv, int h, void* stream) {
   ALPRO_REQUIRE(text && video && tmask && ti && vi && out32 && h % 4 == 0, "alpro_fusion_gather_fwd: bad args");
   const long long total = static_cast<long long>(S) * (L + Nv) * (h / 4);
-  fusion_gather_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(fusion_gather_fwd_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       text, video, reinterpret_cast<const long long*>(tmask), ti, vi, out32, static_cast<uint16_t*>(out16), fmt,
       add_mask, S, L, Nv, h);
   ALPRO_CHECK_LAUNCH("alpro_fusion_gather_fwd");
@@ -1031,7 +1050,7 @@ extern "C" int alpro_fusion_gather_bwd(const float* dout, const int32_t* ti, con
                                        float* dvideo, int S, int L, int Nv, int h, void* stream) {
   ALPRO_REQUIRE(dout && ti && vi && dtext && dvideo, "alpro_fusion_gather_bwd: bad args");
   const long long total = static_cast<long long>(S) * (L + Nv) * h;
-  fusion_gather_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, ti, vi, dtext,
+  launch_k(fusion_gather_bwd_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), dout, ti, vi, dtext,
                                                                                                dvideo, S, L, Nv, h);
   ALPRO_CHECK_LAUNCH("alpro_fusion_gather_bwd");
   return 0;
@@ -1040,7 +1059,7 @@ extern "C" int alpro_fusion_gather_bwd(const float* dout, const int32_t* ti, con
 extern "C" int alpro_cls_mean_fwd(const void* cls_t, void* o, int64_t ldo, int fmt, int B, int T, int S, int d,
                                   const float* frame_weight, void* stream) {
   ALPRO_REQUIRE(cls_t && o, "alpro_cls_mean_fwd: bad args");
-  cls_mean_fwd_kernel<<<grid_for(static_cast<long long>(B) * d, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(cls_mean_fwd_kernel, grid_for(static_cast<long long>(B) * d, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint16_t*>(cls_t), static_cast<uint16_t*>(o), ldo, fmt, B, T, S, d, frame_weight);
   ALPRO_CHECK_LAUNCH("alpro_cls_mean_fwd");
   return 0;
@@ -1048,7 +1067,7 @@ extern "C" int alpro_cls_mean_fwd(const void* cls_t, void* o, int64_t ldo, int f
 
 extern "C" int alpro_dropout_mask(void* out16, int fmt, int64_t n, float p, uint32_t seed, void* stream) {
   ALPRO_REQUIRE(out16 && n > 0 && p >= 0.f && p < 1.f, "alpro_dropout_mask: bad args");
-  dropout_mask_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(dropout_mask_kernel, grid_for((n + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<uint16_t*>(out16), fmt, n, drop_threshold(p), 1.0f / (1.0f - p), seed);
   ALPRO_CHECK_LAUNCH("alpro_dropout_mask");
   return 0;
@@ -1064,7 +1083,7 @@ extern "C" int alpro_patchify_u8(const uint8_t* frames, void* out16, int fmt, in
     of[c] = -mean3[c] / std3[c];
   }
   const long long total = static_cast<long long>(B) * (1 + (H / P) * (W / P) * T) * (3 * P * P / 4);
-  patchify_u8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(patchify_u8_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       frames, static_cast<uint16_t*>(out16), fmt, B, T, H, W, P, sc[0], sc[1], sc[2], of[0], of[1], of[2]);
   ALPRO_CHECK_LAUNCH("alpro_patchify_u8");
   return 0;

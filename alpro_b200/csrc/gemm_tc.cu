@@ -88,6 +88,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();   // the prologue above overlapped the tail of the previous kernel (common.h)
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_work = num_tiles * p.split_k;
@@ -557,7 +558,7 @@ extern "C" int alpro_gemm16(const void* A, const void* B, int64_t M, int64_t N, 
     std::call_once(once, [] {                                                                            \
       cudaFuncSetAttribute(gemm16_kernel<M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
     });                                                                                                  \
-    gemm16_kernel<M_><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);                               \
+    launch_k(gemm16_kernel<M_>, grid, NUM_THREADS, SMEM_BYTES, st, tmA, tmB, p);                               \
   } break;
   switch (mode) {
     ALPRO_LAUNCH_GEMM(E_OUT16)

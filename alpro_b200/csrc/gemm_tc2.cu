@@ -80,6 +80,7 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   cluster_sync_all();   // barrier inits + TMEM allocation visible in both CTAs before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();   // the prologue above overlapped the tail of the previous kernel (common.h)
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;   // tiles of (2*BM) x BN, one per CTA pair
   const int num_work = num_tiles * p.split_k;
@@ -284,7 +285,7 @@ static int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm16_2cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
-  gemm16_2cta_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  launch_k(gemm16_2cta_kernel<MODE>, grid, NUM_THREADS, SMEM_BYTES, st, tmA, tmB, p);
   return 0;
 }
 

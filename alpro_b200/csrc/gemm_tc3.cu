@@ -203,6 +203,7 @@ gemm16_2cta_tma_epi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   cluster_sync_all();   // barrier inits + TMEM allocation visible in both CTAs before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();   // everything above overlapped the tail of the previous kernel; operands are touched below only
 
   // work item = (tile of (2*BM) x BN, K split); split_k > 1 only in E_ATOMIC (out32 += partial products)
   const int num_work = p.num_m_tiles * p.num_n_tiles * p.split_k;
@@ -448,7 +449,7 @@ static int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   std::call_once(once, [] {
     cudaFuncSetAttribute(gemm16_2cta_tma_epi_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
-  gemm16_2cta_tma_epi_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmO, tmO2, tmAux, p);
+  launch_k(gemm16_2cta_tma_epi_kernel<MODE>, grid, NUM_THREADS, SMEM_BYTES, st, tmA, tmB, tmO, tmO2, tmAux, p);
   return 0;
 }
 

@@ -52,6 +52,7 @@ __global__ void small_linear_fwd_kernel(const float* __restrict__ x, long long l
                                         long long ldw, const float* __restrict__ b, float* __restrict__ y,
                                         long long ldy, int M, int N, int K, float alpha, const float* alpha_dev,
                                         int alpha_mode, int relu) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long widx = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (widx >= static_cast<long long>(M) * N) return;
@@ -73,6 +74,7 @@ __global__ void small_linear_dx_kernel(const float* __restrict__ dy, long long l
                                        long long ldya, const float* __restrict__ W, long long ldw,
                                        float* __restrict__ dx, long long lddx, int M, int N, int K, float alpha,
                                        const float* alpha_dev, int alpha_mode, int accumulate) {
+  pdl_grid_sync();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (k >= K) return;
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(256) small_linear_dx_split_kernel(const float*
                                                                     const float* __restrict__ W, long long ldw,
                                                                     float* __restrict__ dx, long long lddx, int N, int K,
                                                                     float alpha, const float* alpha_dev, int alpha_mode) {
+  pdl_grid_sync();
   __shared__ float4 part[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int m = blockIdx.y;
@@ -131,6 +134,7 @@ __global__ void small_linear_dw_kernel(const float* __restrict__ dy, long long l
                                        float* __restrict__ dW, long long lddw, float* __restrict__ db, int M, int N,
                                        int K, float alpha, const float* alpha_dev, int alpha_mode, float out_scale,
                                        int accumulate) {
+  pdl_grid_sync();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (k >= K) return;
@@ -151,6 +155,7 @@ __global__ void small_linear_dw_kernel(const float* __restrict__ dy, long long l
 // y = x / max(||x||, eps)   (F.normalize, alpro_models.py:103,205,750,761); one warp per row
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norm, int M,
                                   int d, float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -163,6 +168,7 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
 // dx = (dy - y (y . dy)) / norm       (exact when norm > eps, which holds for any non-degenerate feature)
 __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                   const float* __restrict__ norm, float* __restrict__ dx, int M, int d) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -181,6 +187,7 @@ __global__ void softmax_ce_fwd_kernel(const float* __restrict__ logits, long lon
                                       long long ld_soft, const uint8_t* __restrict__ row_ignore,
                                       float* __restrict__ row_loss, float* __restrict__ row_lse,
                                       float* __restrict__ row_valid, float* __restrict__ row_tsum) {
+  pdl_grid_sync();
   __shared__ float red[32];
   const int r = blockIdx.x;
   const float* x = logits + r * ld;
@@ -217,6 +224,7 @@ __global__ void softmax_ce_fwd_kernel(const float* __restrict__ logits, long lon
 // loss = sum_r row_loss / denom,  denom = denom_mode 0: #valid rows ; 1: R (plain mean over all rows)
 __global__ void loss_reduce_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_valid, int R,
                                    int denom_mode, float* __restrict__ loss_out, float* __restrict__ denom_out) {
+  pdl_grid_sync();
   __shared__ float red[32];
   float s = 0.f, v = 0.f;
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
@@ -240,6 +248,7 @@ __global__ void softmax_ce_bwd_kernel(const float* __restrict__ logits, long lon
                                       const float* __restrict__ denom, const float* __restrict__ gptr, float gscale,
                                       float* __restrict__ out32, uint16_t* __restrict__ out16, int fmt,
                                       long long ld_out, int C_out) {
+  pdl_grid_sync();
   const int r = blockIdx.x;
   const float* x = logits + r * ld;
   const float coef = gscale * (gptr ? *gptr : 1.f) * row_valid[r] / (*denom);
@@ -260,6 +269,7 @@ __global__ void softmax_ce_bwd_kernel(const float* __restrict__ logits, long lon
 __global__ void temp_grad_kernel(const float* __restrict__ dsa, const float* __restrict__ sa, long long na,
                                  const float* __restrict__ dsb, const float* __restrict__ sb, long long nb,
                                  const float* __restrict__ temp, float* __restrict__ dtemp, float coef) {
+  pdl_grid_sync();
   __shared__ float red[32];
   float s = 0.f;
   for (long long i = threadIdx.x; i < na; i += blockDim.x) s += dsa[i] * sa[i];
@@ -268,12 +278,14 @@ __global__ void temp_grad_kernel(const float* __restrict__ dsa, const float* __r
   if (threadIdx.x == 0) *dtemp += -coef * s / (*temp);
 }
 
-__global__ void clamp_scalar_kernel(float* p, float lo, float hi) { *p = fminf(fmaxf(*p, lo), hi); }
+__global__ void clamp_scalar_kernel(float* p, float lo, float hi) {
+  pdl_grid_sync(); *p = fminf(fmaxf(*p, lo), hi); }
 
 // ------------------------------------------------------------------------------------------------ MPM pooling
 // pooled[b] = sum_n w[b,n] x[b, row0 + n] / sum_n w[b,n],  w = 1 - patch_mask   (alpro_models.py:214-224)
 __global__ void masked_mean_fwd_kernel(const float* __restrict__ x, long long seq_stride, int row0,
                                        const float* __restrict__ patch_mask, int Np, int h, float* __restrict__ out) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   float cnt = 0.f;
   for (int n = 0; n < Np; ++n) cnt += 1.f - patch_mask[b * Np + n];
@@ -285,6 +297,7 @@ __global__ void masked_mean_fwd_kernel(const float* __restrict__ x, long long se
 }
 __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ patch_mask, int Np,
                                        int h, float* __restrict__ dx, long long seq_stride, int row0) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   float cnt = 0.f;
   for (int n = 0; n < Np; ++n) cnt += 1.f - patch_mask[b * Np + n];
@@ -299,6 +312,7 @@ __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, const flo
 // out[i, l, :] = src[(s0 + i), l, :] for l < L (first L rows of each R-row sequence)     (mlm txt_output, :366-367)
 __global__ void take_rows_fwd_kernel(const float* __restrict__ src, int R, int s0, int n, int L, int h,
                                      float* __restrict__ out32, uint16_t* __restrict__ out16, int fmt) {
+  pdl_grid_sync();
   const long long total = static_cast<long long>(n) * L * h;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -312,6 +326,7 @@ __global__ void take_rows_fwd_kernel(const float* __restrict__ src, int R, int s
 }
 __global__ void take_rows_bwd_kernel(const float* __restrict__ dout, int R, int s0, int n, int L, int h,
                                      float* __restrict__ dsrc) {
+  pdl_grid_sync();
   const long long total = static_cast<long long>(n) * L * h;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -326,6 +341,7 @@ __global__ void take_rows_bwd_kernel(const float* __restrict__ dout, int R, int 
 // (alpro_models.py:288-299, 819-828); one warp per row
 __global__ void neg_weights_kernel(const float* __restrict__ sim, long long ld, int col0, int b,
                                    float* __restrict__ w) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= b) return;
@@ -346,6 +362,7 @@ __global__ void neg_weights_kernel(const float* __restrict__ sim, long long ld, 
 // (counter = (row, draw, 0, 0), key = seed). The index is a device int64; nothing returns to the host.
 __global__ void neg_sample_kernel(const float* __restrict__ sim, long long ld, int col0, int b, uint32_t seed_lo,
                                   uint32_t seed_hi, uint32_t draw, float* __restrict__ w, long long* __restrict__ idx) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= b) return;
@@ -385,6 +402,7 @@ __global__ void neg_sample_kernel(const float* __restrict__ sim, long long ld, i
 }
 
 __global__ void philox_kat_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Philox4 v = philox4x32_10(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5]);
@@ -394,6 +412,7 @@ __global__ void philox_kat_kernel(const uint32_t* __restrict__ in, uint32_t* __r
 // out16 = dy * dact, dact = gelu'(pre) saved by the forward GEMM epilogue   (MLM transform backward, xbert.py:659-661)
 __global__ void gelu_grad_mul_kernel(const float* __restrict__ dy, const uint16_t* __restrict__ pre, int pre_fmt,
                                      uint16_t* __restrict__ out, int out_fmt, long long n) {
+  pdl_grid_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = f32_to_16(dy[i] * f16_to_32(pre[i], pre_fmt), out_fmt);
@@ -403,6 +422,7 @@ __global__ void gelu_grad_mul_kernel(const float* __restrict__ dy, const uint16_
 // ignore = (argmax index < 0.2)  i.e. argmax == 0 (reference behaviour kept bug-compatible).
 __global__ void pseudo_labels_kernel(const float* __restrict__ sim, int C, float* __restrict__ soft,
                                      uint8_t* __restrict__ ignore) {
+  pdl_grid_sync();
   __shared__ float red[32];
   __shared__ int redi[32];
   const int r = blockIdx.x;
@@ -464,7 +484,7 @@ extern "C" int alpro_small_linear_fwd(const float* x, int64_t ldx, const float* 
   ALPRO_REQUIRE(x && W && y && M > 0 && N > 0 && K > 0, "alpro_small_linear_fwd: bad args");
   ALPRO_REQUIRE(alpha_mode == 0 || alpha_dev, "alpro_small_linear_fwd: alpha_dev missing");
   const long long warps = static_cast<long long>(M) * N;
-  small_linear_fwd_kernel<<<static_cast<unsigned>(cdiv(warps, 8)), 256, 0, ST>>>(x, ldx, W, ldw, b, y, ldy, M, N, K,
+  launch_k(small_linear_fwd_kernel, static_cast<unsigned>(cdiv(warps, 8)), 256, 0, ST, x, ldx, W, ldw, b, y, ldy, M, N, K,
                                                                                  alpha, alpha_dev, alpha_mode, relu);
   ALPRO_CHECK_LAUNCH("alpro_small_linear_fwd");
   return 0;
@@ -488,11 +508,11 @@ extern "C" int alpro_small_linear_bwd(const float* dy, int64_t lddy, const float
         }
       }
       dim3 grid(static_cast<unsigned>(cdiv(K, 128)), M, static_cast<unsigned>(cdiv(N, 64)));
-      small_linear_dx_split_kernel<<<grid, 256, 0, ST>>>(dy, lddy, yact, ldya, W, ldw, dx, lddx, N, K, alpha, alpha_dev,
+      launch_k(small_linear_dx_split_kernel, grid, 256, 0, ST, dy, lddy, yact, ldya, W, ldw, dx, lddx, N, K, alpha, alpha_dev,
                                                          alpha_mode);
     } else {
       dim3 grid(static_cast<unsigned>(cdiv(K, 128)), M);
-      small_linear_dx_kernel<<<grid, 128, 0, ST>>>(dy, lddy, yact, ldya, W, ldw, dx, lddx, M, N, K, alpha, alpha_dev,
+      launch_k(small_linear_dx_kernel, grid, 128, 0, ST, dy, lddy, yact, ldya, W, ldw, dx, lddx, M, N, K, alpha, alpha_dev,
                                                    alpha_mode, dx_accumulate);
     }
     ALPRO_CHECK_LAUNCH("alpro_small_linear_bwd(dx)");
@@ -500,7 +520,7 @@ extern "C" int alpro_small_linear_bwd(const float* dy, int64_t lddy, const float
   if (dW) {
     ALPRO_REQUIRE(x, "alpro_small_linear_bwd: x needed for dW");
     dim3 grid(static_cast<unsigned>(cdiv(K, 128)), N);
-    small_linear_dw_kernel<<<grid, 128, 0, ST>>>(dy, lddy, yact, ldya, x, ldx, dW, lddw, db, M, N, K, alpha, alpha_dev,
+    launch_k(small_linear_dw_kernel, grid, 128, 0, ST, dy, lddy, yact, ldya, x, ldx, dW, lddw, db, M, N, K, alpha, alpha_dev,
                                                  alpha_mode, dw_scale, dw_accumulate);
     ALPRO_CHECK_LAUNCH("alpro_small_linear_bwd(dW)");
   }
@@ -509,14 +529,14 @@ extern "C" int alpro_small_linear_bwd(const float* dy, int64_t lddy, const float
 
 extern "C" int alpro_l2norm_fwd(const float* x, float* y, float* norm, int M, int d, float eps, void* stream) {
   ALPRO_REQUIRE(x && y && norm && M > 0, "alpro_l2norm_fwd: bad args");
-  l2norm_fwd_kernel<<<static_cast<unsigned>(cdiv(M, 4)), 128, 0, ST>>>(x, y, norm, M, d, eps);
+  launch_k(l2norm_fwd_kernel, static_cast<unsigned>(cdiv(M, 4)), 128, 0, ST, x, y, norm, M, d, eps);
   ALPRO_CHECK_LAUNCH("alpro_l2norm_fwd");
   return 0;
 }
 extern "C" int alpro_l2norm_bwd(const float* dy, const float* y, const float* norm, float* dx, int M, int d,
                                 void* stream) {
   ALPRO_REQUIRE(dy && y && norm && dx && M > 0, "alpro_l2norm_bwd: bad args");
-  l2norm_bwd_kernel<<<static_cast<unsigned>(cdiv(M, 4)), 128, 0, ST>>>(dy, y, norm, dx, M, d);
+  launch_k(l2norm_bwd_kernel, static_cast<unsigned>(cdiv(M, 4)), 128, 0, ST, dy, y, norm, dx, M, d);
   ALPRO_CHECK_LAUNCH("alpro_l2norm_bwd");
   return 0;
 }
@@ -527,10 +547,10 @@ extern "C" int alpro_softmax_ce_fwd(const float* logits, int64_t ld, int R, int 
                                     float* denom_out, void* stream) {
   ALPRO_REQUIRE(logits && (hard || soft) && row_loss && row_lse && row_valid && row_tsum && loss_out && denom_out && R > 0,
                 "alpro_softmax_ce_fwd: bad args");
-  softmax_ce_fwd_kernel<<<R, 256, 0, ST>>>(logits, ld, C, reinterpret_cast<const long long*>(hard), soft, ld_soft,
+  launch_k(softmax_ce_fwd_kernel, R, 256, 0, ST, logits, ld, C, reinterpret_cast<const long long*>(hard), soft, ld_soft,
                                            row_ignore, row_loss, row_lse, row_valid, row_tsum);
   ALPRO_CHECK_LAUNCH("alpro_softmax_ce_fwd");
-  loss_reduce_kernel<<<1, 256, 0, ST>>>(row_loss, row_valid, R, denom_mode, loss_out, denom_out);
+  launch_k(loss_reduce_kernel, 1, 256, 0, ST, row_loss, row_valid, R, denom_mode, loss_out, denom_out);
   ALPRO_CHECK_LAUNCH("alpro_softmax_ce_fwd(reduce)");
   return 0;
 }
@@ -541,7 +561,7 @@ extern "C" int alpro_softmax_ce_bwd(const float* logits, int64_t ld, int R, int 
                                     float* out32, void* out16, int out16_fmt, int64_t ld_out, int C_out, void* stream) {
   ALPRO_REQUIRE(logits && (hard || soft) && row_lse && row_valid && row_tsum && denom && (out32 || out16) && C_out >= C,
                 "alpro_softmax_ce_bwd: bad args");
-  softmax_ce_bwd_kernel<<<R, 256, 0, ST>>>(logits, ld, C, reinterpret_cast<const long long*>(hard), soft, ld_soft,
+  launch_k(softmax_ce_bwd_kernel, R, 256, 0, ST, logits, ld, C, reinterpret_cast<const long long*>(hard), soft, ld_soft,
                                            row_lse, row_valid, row_tsum, denom, gptr, gscale, out32,
                                            static_cast<uint16_t*>(out16), out16_fmt, ld_out, C_out);
   ALPRO_CHECK_LAUNCH("alpro_softmax_ce_bwd");
@@ -551,14 +571,14 @@ extern "C" int alpro_softmax_ce_bwd(const float* logits, int64_t ld, int R, int 
 extern "C" int alpro_temp_grad(const float* dsa, const float* sa, int64_t na, const float* dsb, const float* sb,
                                int64_t nb, const float* temp, float* dtemp, float coef, void* stream) {
   ALPRO_REQUIRE(dsa && sa && temp && dtemp, "alpro_temp_grad: bad args");
-  temp_grad_kernel<<<1, 256, 0, ST>>>(dsa, sa, na, dsb, sb, dsb ? nb : 0, temp, dtemp, coef);
+  launch_k(temp_grad_kernel, 1, 256, 0, ST, dsa, sa, na, dsb, sb, dsb ? nb : 0, temp, dtemp, coef);
   ALPRO_CHECK_LAUNCH("alpro_temp_grad");
   return 0;
 }
 
 extern "C" int alpro_clamp_scalar(float* p, float lo, float hi, void* stream) {
   ALPRO_REQUIRE(p, "alpro_clamp_scalar: null");
-  clamp_scalar_kernel<<<1, 1, 0, ST>>>(p, lo, hi);
+  launch_k(clamp_scalar_kernel, 1, 1, 0, ST, p, lo, hi);
   ALPRO_CHECK_LAUNCH("alpro_clamp_scalar");
   return 0;
 }
@@ -566,14 +586,14 @@ extern "C" int alpro_clamp_scalar(float* p, float lo, float hi, void* stream) {
 extern "C" int alpro_masked_mean_fwd(const float* x, int64_t seq_stride, int row0, const float* patch_mask, int B,
                                      int Np, int h, float* out, void* stream) {
   ALPRO_REQUIRE(x && patch_mask && out && B > 0, "alpro_masked_mean_fwd: bad args");
-  masked_mean_fwd_kernel<<<B, 256, 0, ST>>>(x, seq_stride, row0, patch_mask, Np, h, out);
+  launch_k(masked_mean_fwd_kernel, B, 256, 0, ST, x, seq_stride, row0, patch_mask, Np, h, out);
   ALPRO_CHECK_LAUNCH("alpro_masked_mean_fwd");
   return 0;
 }
 extern "C" int alpro_masked_mean_bwd(const float* dout, const float* patch_mask, int B, int Np, int h, float* dx,
                                      int64_t seq_stride, int row0, void* stream) {
   ALPRO_REQUIRE(dout && patch_mask && dx && B > 0, "alpro_masked_mean_bwd: bad args");
-  masked_mean_bwd_kernel<<<B, 256, 0, ST>>>(dout, patch_mask, Np, h, dx, seq_stride, row0);
+  launch_k(masked_mean_bwd_kernel, B, 256, 0, ST, dout, patch_mask, Np, h, dx, seq_stride, row0);
   ALPRO_CHECK_LAUNCH("alpro_masked_mean_bwd");
   return 0;
 }
@@ -581,21 +601,21 @@ extern "C" int alpro_masked_mean_bwd(const float* dout, const float* patch_mask,
 extern "C" int alpro_take_rows_fwd(const float* src, int R, int s0, int n, int L, int h, float* out32, void* out16,
                                    int fmt, void* stream) {
   ALPRO_REQUIRE(src && (out32 || out16) && n > 0, "alpro_take_rows_fwd: bad args");
-  take_rows_fwd_kernel<<<grid_for(static_cast<long long>(n) * L * h, 256), 256, 0, ST>>>(
+  launch_k(take_rows_fwd_kernel, grid_for(static_cast<long long>(n) * L * h, 256), 256, 0, ST, 
       src, R, s0, n, L, h, out32, static_cast<uint16_t*>(out16), fmt);
   ALPRO_CHECK_LAUNCH("alpro_take_rows_fwd");
   return 0;
 }
 extern "C" int alpro_take_rows_bwd(const float* dout, int R, int s0, int n, int L, int h, float* dsrc, void* stream) {
   ALPRO_REQUIRE(dout && dsrc && n > 0, "alpro_take_rows_bwd: bad args");
-  take_rows_bwd_kernel<<<grid_for(static_cast<long long>(n) * L * h, 256), 256, 0, ST>>>(dout, R, s0, n, L, h, dsrc);
+  launch_k(take_rows_bwd_kernel, grid_for(static_cast<long long>(n) * L * h, 256), 256, 0, ST, dout, R, s0, n, L, h, dsrc);
   ALPRO_CHECK_LAUNCH("alpro_take_rows_bwd");
   return 0;
 }
 
 extern "C" int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, float* w, void* stream) {
   ALPRO_REQUIRE(sim && w && b > 0, "alpro_neg_weights: bad args");
-  neg_weights_kernel<<<static_cast<unsigned>(cdiv(b, 4)), 128, 0, ST>>>(sim, ld, col0, b, w);
+  launch_k(neg_weights_kernel, static_cast<unsigned>(cdiv(b, 4)), 128, 0, ST, sim, ld, col0, b, w);
   ALPRO_CHECK_LAUNCH("alpro_neg_weights");
   return 0;
 }
@@ -603,7 +623,7 @@ extern "C" int alpro_neg_weights(const float* sim, int64_t ld, int col0, int b, 
 extern "C" int alpro_neg_sample(const float* sim, int64_t ld, int col0, int b, uint32_t seed_lo, uint32_t seed_hi,
                                 uint32_t draw, float* w, int64_t* idx, void* stream) {
   ALPRO_REQUIRE(sim && idx && b > 0, "alpro_neg_sample: bad args");
-  neg_sample_kernel<<<static_cast<unsigned>(cdiv(b, 4)), 128, 0, ST>>>(sim, ld, col0, b, seed_lo, seed_hi, draw, w,
+  launch_k(neg_sample_kernel, static_cast<unsigned>(cdiv(b, 4)), 128, 0, ST, sim, ld, col0, b, seed_lo, seed_hi, draw, w,
                                                                       reinterpret_cast<long long*>(idx));
   ALPRO_CHECK_LAUNCH("alpro_neg_sample");
   return 0;
@@ -611,7 +631,7 @@ extern "C" int alpro_neg_sample(const float* sim, int64_t ld, int col0, int b, u
 
 extern "C" int alpro_philox4x32_10(const uint32_t* ctr_key, uint32_t* out, int n, void* stream) {
   ALPRO_REQUIRE(ctr_key && out && n > 0, "alpro_philox4x32_10: bad args");
-  philox_kat_kernel<<<static_cast<unsigned>(cdiv(n, 128)), 128, 0, ST>>>(ctr_key, out, n);
+  launch_k(philox_kat_kernel, static_cast<unsigned>(cdiv(n, 128)), 128, 0, ST, ctr_key, out, n);
   ALPRO_CHECK_LAUNCH("alpro_philox4x32_10");
   return 0;
 }
@@ -619,7 +639,7 @@ extern "C" int alpro_philox4x32_10(const uint32_t* ctr_key, uint32_t* out, int n
 extern "C" int alpro_gelu_grad_mul(const float* dy, const void* pre, int pre_fmt, void* out, int out_fmt, int64_t n,
                                    void* stream) {
   ALPRO_REQUIRE(dy && pre && out && n > 0, "alpro_gelu_grad_mul: bad args");
-  gelu_grad_mul_kernel<<<grid_for(n, 256), 256, 0, ST>>>(dy, static_cast<const uint16_t*>(pre), pre_fmt,
+  launch_k(gelu_grad_mul_kernel, grid_for(n, 256), 256, 0, ST, dy, static_cast<const uint16_t*>(pre), pre_fmt,
                                                          static_cast<uint16_t*>(out), out_fmt, n);
   ALPRO_CHECK_LAUNCH("alpro_gelu_grad_mul");
   return 0;
@@ -627,7 +647,7 @@ extern "C" int alpro_gelu_grad_mul(const float* dy, const void* pre, int pre_fmt
 
 extern "C" int alpro_pseudo_labels(const float* sim, int R, int C, float* soft, uint8_t* ignore, void* stream) {
   ALPRO_REQUIRE(sim && soft && ignore && R > 0 && C > 0, "alpro_pseudo_labels: bad args");
-  pseudo_labels_kernel<<<R, 256, 0, ST>>>(sim, C, soft, ignore);
+  launch_k(pseudo_labels_kernel, R, 256, 0, ST, sim, C, soft, ignore);
   ALPRO_CHECK_LAUNCH("alpro_pseudo_labels");
   return 0;
 }

@@ -8,6 +8,7 @@ namespace alpro {
 namespace {
 
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ float red[32];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -34,6 +35,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
 // g is first scaled by the clip coefficient min(1, max_norm / (||g|| + 1e-6)) when max_norm > 0.
 __global__ void adamw_prepare_kernel(const float* __restrict__ gnorm_sq, float lr, float beta1, float beta2,
                                      int correct_bias, int* __restrict__ step_count, float* __restrict__ out) {
+  pdl_grid_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (!isfinite(*gnorm_sq)) { *out = 0.f; return; }
   const int t = ++*step_count;
@@ -46,6 +48,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ v, long long n, float beta1, float beta2, float eps, float step_size,
                              const float* __restrict__ step_size_dev, float lr_wd, const float* __restrict__ gnorm_sq,
                              float max_norm) {
+  pdl_grid_sync();
   float clip = 1.f;
   if (gnorm_sq && !isfinite(*gnorm_sq)) return;   // fp16 gradient overflow: skip this update (dynamic loss scaling)
   if (step_size_dev) step_size = *step_size_dev;
@@ -85,7 +88,7 @@ extern "C" int alpro_sumsq(const float* x, int64_t n, float* out, void* stream) 
   ALPRO_REQUIRE(x && out && n > 0 && aligned16(x), "alpro_sumsq: bad args");
   long long g = cdiv(cdiv(n, 4), 256);
   if (g > num_sms() * 8) g = num_sms() * 8;
-  sumsq_kernel<<<static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  launch_k(sumsq_kernel, static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream), x, n, out);
   ALPRO_CHECK_LAUNCH("alpro_sumsq");
   return 0;
 }
@@ -97,7 +100,7 @@ extern "C" int alpro_adamw_step(float* p, const float* g, float* m, float* v, in
   ALPRO_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "alpro_adamw_step: alignment");
   long long gr = cdiv(n / 4, 256);
   if (gr > num_sms() * 8) gr = num_sms() * 8;
-  adamw_kernel<<<static_cast<unsigned>(gr), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
+  launch_k(adamw_kernel, static_cast<unsigned>(gr), 256, 0, static_cast<cudaStream_t>(stream), p, g, m, v, n, beta1, beta2, eps,
                                                                                         step_size, nullptr, lr_wd,
                                                                                         gnorm_sq, max_norm);
   ALPRO_CHECK_LAUNCH("alpro_adamw_step");
@@ -107,7 +110,7 @@ extern "C" int alpro_adamw_step(float* p, const float* g, float* m, float* v, in
 extern "C" int alpro_adamw_prepare(const float* gnorm_sq, float lr, float beta1, float beta2, int correct_bias,
                                    int* step_count, float* step_size_out, void* stream) {
   ALPRO_REQUIRE(gnorm_sq && step_count && step_size_out, "alpro_adamw_prepare: bad args");
-  adamw_prepare_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(gnorm_sq, lr, beta1, beta2, correct_bias,
+  launch_k(adamw_prepare_kernel, 1, 32, 0, static_cast<cudaStream_t>(stream), gnorm_sq, lr, beta1, beta2, correct_bias,
                                                                        step_count, step_size_out);
   ALPRO_CHECK_LAUNCH("alpro_adamw_prepare");
   return 0;
@@ -120,7 +123,7 @@ extern "C" int alpro_adamw_step_dev(float* p, const float* g, float* m, float* v
   ALPRO_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "alpro_adamw_step_dev: alignment");
   long long gr = cdiv(n / 4, 256);
   if (gr > num_sms() * 8) gr = num_sms() * 8;
-  adamw_kernel<<<static_cast<unsigned>(gr), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
+  launch_k(adamw_kernel, static_cast<unsigned>(gr), 256, 0, static_cast<cudaStream_t>(stream), p, g, m, v, n, beta1, beta2, eps,
                                                                                         0.f, step_size_dev, lr_wd,
                                                                                         gnorm_sq, max_norm);
   ALPRO_CHECK_LAUNCH("alpro_adamw_step_dev");

@@ -152,6 +152,7 @@ tattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_grid_sync();   // prologue done; global memory is touched below only (common.h)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -369,6 +370,7 @@ tattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_grid_sync();   // prologue done; global memory is touched below only (common.h)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -608,10 +610,10 @@ int forward(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int B, i
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   if (fmt == 1) {
     cudaFuncSetAttribute(fwd::tattn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_BYTES);
-    fwd::tattn_fwd_tc_kernel<true><<<grid, fwd::THREADS, fwd::SMEM_BYTES, st>>>(tq, to, p);
+    launch_k(fwd::tattn_fwd_tc_kernel<true>, grid, fwd::THREADS, fwd::SMEM_BYTES, st, tq, to, p);
   } else {
     cudaFuncSetAttribute(fwd::tattn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_BYTES);
-    fwd::tattn_fwd_tc_kernel<false><<<grid, fwd::THREADS, fwd::SMEM_BYTES, st>>>(tq, to, p);
+    launch_k(fwd::tattn_fwd_tc_kernel<false>, grid, fwd::THREADS, fwd::SMEM_BYTES, st, tq, to, p);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -639,10 +641,10 @@ int backward(const void* qkv, int64_t ld_qkv, const void* dout, int64_t ld_dout,
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   if (fmt == 1) {
     cudaFuncSetAttribute(bwd::tattn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
-    bwd::tattn_bwd_tc_kernel<true><<<grid, bwd::THREADS, bwd::SMEM_BYTES, st>>>(tq, tg, td, p);
+    launch_k(bwd::tattn_bwd_tc_kernel<true>, grid, bwd::THREADS, bwd::SMEM_BYTES, st, tq, tg, td, p);
   } else {
     cudaFuncSetAttribute(bwd::tattn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
-    bwd::tattn_bwd_tc_kernel<false><<<grid, bwd::THREADS, bwd::SMEM_BYTES, st>>>(tq, tg, td, p);
+    launch_k(bwd::tattn_bwd_tc_kernel<false>, grid, bwd::THREADS, bwd::SMEM_BYTES, st, tq, tg, td, p);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -86,7 +86,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for l in self.lines:
             parts = [x.strip() for x in l.split(",")]
@@ -97,12 +97,53 @@ class ClockSampler:
                 mx.append(float(parts[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(parts[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_median": pw[len(pw) // 2] if pw else None}
+
+
+class EnergyMeter:
+    """Board energy over a timed region from the NVML energy counter (mJ since driver load): joules per step and the
+    average power against the enforced power limit. avg_w ~ limit_w with `sw_power_cap` active means the step is
+    energy-bound: its duration is joules / limit, whatever the kernel durations add up to."""
+
+    def __init__(self, index=0):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1e3
+        except Exception:
+            self.h = None
+
+    def read(self):
+        if self.h is None:
+            return None
+        try:
+            return self.nv.nvmlDeviceGetTotalEnergyConsumption(self.h) / 1e3, time.perf_counter()
+        except Exception:
+            return None
+
+    def report(self, a, b, steps, flop_per_step=None):
+        if a is None or b is None or b[1] <= a[1]:
+            return None
+        joules, secs = b[0] - a[0], b[1] - a[1]
+        out = {"joules_per_step": round(joules / steps, 2), "avg_w": round(joules / secs, 1),
+               "limit_w": round(self.limit_w, 1), "window_s": round(secs, 3),
+               "source": "nvmlDeviceGetTotalEnergyConsumption around the timed region (host clock window)"}
+        if flop_per_step:
+            out["pj_per_flop_whole_step"] = round(joules / steps / flop_per_step * 1e12, 3)
+        return out
 
 
 def make_batch(kind, B, seed, device, pinned=False):
@@ -257,9 +298,13 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     calls0 = _lib.counted.calls
+    meter = EnergyMeter(D.local) if rank == 0 else None
+    en0 = meter.read() if meter else None
     ms_step = D.timed(lambda: step(dev_batch), args.steps, host_ms, "step")
+    en1 = meter.read() if meter else None
     launches = (_lib.counted.calls - calls0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
+    power = meter.report(en0, en1, args.steps, FLOP_PER_PAIR[kind] * B) if meter else None
     e2e_step()
     ms_e2e = D.timed(e2e_step, args.steps)
 
@@ -361,6 +406,7 @@ def run_ours(args):
                          "launches with ~1/32 of the device work = upper bound of the per-step host cost"},
         "ms_per_step_with_fused_adamw": round(ms_opt, 3) if ms_opt else None,
         "clocks": clocks,
+        "power": power,
         "roofline": {"bound": "tensor", "kernel": "gemm16 (tcgen05, all launches of one step)",
                      "achieved": round(achieved, 1),
                      "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["sustained"], 4),
