@@ -849,6 +849,18 @@ inline int grid_for(long long work_items, int block) {
 
 using namespace alpro;
 
+namespace alpro {
+int layernorm_fwd_bulk(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, int64_t M, int d,
+                       float* out32, int64_t ld32, void* out16, int64_t ld16, int out16_fmt, float* mean, float* rstd,
+                       const void* mul16, cudaStream_t st);
+int layernorm_bwd_bulk(const void* dy, int dy_kind, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                       const float* rstd, const float* gamma, int64_t M, int d, float* dx32, int64_t lddx, int accumulate,
+                       void* dx16, int64_t lddx16, int dx16_fmt, int zero_period, float* dgamma, float* dbeta,
+                       float param_scale, float* colsum, int colsum_zero_period, const void* dy_mul16,
+                       const void* dx16_mul16, const float* dx16_row_scale, const float* colsum_row_scale,
+                       cudaStream_t st);
+}
+
 extern "C" int alpro_cast_f32_to_16(const float* src, void* dst, int64_t n, int fmt, void* stream) {
   ALPRO_REQUIRE(src && dst && n >= 0, "alpro_cast_f32_to_16: bad args");
   if (n == 0) return 0;
@@ -874,6 +886,11 @@ extern "C" int alpro_layernorm_fwd(const float* x, int64_t ldx, const float* gam
   ALPRO_REQUIRE(x && gamma && beta && M > 0, "alpro_layernorm_fwd: bad args");
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_fwd: d=%d unsupported (multiple of 4, <= 1024)", d);
   ALPRO_REQUIRE(ldx % 4 == 0 && (!out32 || ld32 % 4 == 0) && (!out16 || ld16 % 4 == 0), "alpro_layernorm_fwd: ld");
+  if (layernorm_fwd_bulk(x, ldx, gamma, beta, eps, M, d, out32, ld32, out16, ld16, out16_fmt, mean, rstd, mul16,
+                         static_cast<cudaStream_t>(stream)) == ALPRO_OK) {
+    ALPRO_CHECK_LAUNCH("alpro_layernorm_fwd(bulk)");
+    return 0;
+  }
   const int wpb = 8;
   launch_k(layernorm_fwd_kernel, static_cast<unsigned>(cdiv(M, wpb)), wpb * 32, 0, static_cast<cudaStream_t>(stream), 
       x, ldx, gamma, beta, eps, M, d, out32, ld32, static_cast<uint16_t*>(out16), ld16, out16_fmt, mean, rstd,
@@ -893,6 +910,13 @@ extern "C" int alpro_layernorm_bwd(const void* dy, int dy_kind, int64_t lddy, co
   ALPRO_REQUIRE(d % 4 == 0 && d <= LN_MAX_V4 * 128, "alpro_layernorm_bwd: d=%d unsupported", d);
   ALPRO_REQUIRE(dy_kind >= 0 && dy_kind <= 2, "alpro_layernorm_bwd: dy_kind");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // d = 768 token streams without multiplier rows: bulk-copy pipeline with packed fp32 math (layernorm_bulk.cu)
+  if (layernorm_bwd_bulk(dy, dy_kind, lddy, x, ldx, mean, rstd, gamma, M, d, dx32, lddx, accumulate, dx16, lddx16, dx16_fmt,
+                         zero_period, dgamma, dbeta, param_scale, colsum, colsum_zero_period, dy_mul16, dx16_mul16,
+                         dx16_row_scale, colsum_row_scale, st) == ALPRO_OK) {
+    ALPRO_CHECK_LAUNCH("alpro_layernorm_bwd(bulk)");
+    return 0;
+  }
   // Large row counts (the video token stream): one 12-warp block per SM with cp.async double buffering.
   // ALPRO_LN_BWD_ASYNC=0 keeps the register/occupancy version (read per call).
   {

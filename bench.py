@@ -139,8 +139,9 @@ class EnergyMeter:
             return None
         joules, secs = b[0] - a[0], b[1] - a[1]
         out = {"joules_per_step": round(joules / steps, 2), "avg_w": round(joules / secs, 1),
-               "limit_w": round(self.limit_w, 1), "window_s": round(secs, 3),
-               "source": "nvmlDeviceGetTotalEnergyConsumption around the timed region (host clock window)"}
+               "limit_w": round(self.limit_w, 1), "window_s": round(secs, 3), "steps": steps,
+               "ms_per_step_in_window": round(secs / steps * 1e3, 3),
+               "source": "nvmlDeviceGetTotalEnergyConsumption around a synchronised run of the same step"}
         if flop_per_step:
             out["pj_per_flop_whole_step"] = round(joules / steps / flop_per_step * 1e12, 3)
         return out
@@ -298,13 +299,22 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     calls0 = _lib.counted.calls
-    meter = EnergyMeter(D.local) if rank == 0 else None
-    en0 = meter.read() if meter else None
     ms_step = D.timed(lambda: step(dev_batch), args.steps, host_ms, "step")
-    en1 = meter.read() if meter else None
     launches = (_lib.counted.calls - calls0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
-    power = meter.report(en0, en1, args.steps, FLOP_PER_PAIR[kind] * B) if meter else None
+    # board energy of the same step, measured after the timed region over a longer window (the NVML counter updates every
+    # ~100 ms: 30+ steps keep the two end-point errors below a few percent); the window is bracketed by synchronize()
+    power = None
+    meter = EnergyMeter(D.local) if rank == 0 else None
+    if meter is not None and meter.h is not None:
+        n_en = max(args.steps, 30)
+        torch.cuda.synchronize()
+        en0 = meter.read()
+        for _ in range(n_en):
+            step(dev_batch)
+        torch.cuda.synchronize()
+        en1 = meter.read()
+        power = meter.report(en0, en1, n_en, FLOP_PER_PAIR[kind] * B)
     e2e_step()
     ms_e2e = D.timed(e2e_step, args.steps)
 

@@ -127,12 +127,15 @@ def test_gemm16(case, gemm_impl):
 
 
 # ------------------------------------------------------------------------------------------------------------ LN
-@pytest.mark.parametrize("ln_async", ["1", "0"])
-@pytest.mark.parametrize("d,eps,M", [(768, 1e-6, 333), (192, 1e-12, 333), (768, 1e-6, 4099), (256, 1e-6, 21000)])
-def test_layernorm_fwd_bwd(d, eps, M, ln_async, monkeypatch):
-    """M >= 4096 takes the cp.async double-buffered backward (one 12-warp block per SM), smaller M — or
-    ALPRO_LN_BWD_ASYNC=0 — the register one."""
-    monkeypatch.setenv("ALPRO_LN_BWD_ASYNC", ln_async)
+@pytest.mark.parametrize("ln_path", ["bulk", "async", "reg"])
+@pytest.mark.parametrize("d,eps,M", [(768, 1e-6, 333), (192, 1e-12, 333), (768, 1e-6, 4099), (256, 1e-6, 21000),
+                                     (768, 1e-6, 9001)])
+def test_layernorm_fwd_bwd(d, eps, M, ln_path, monkeypatch):
+    """M >= 4096 and d = 768 takes the bulk-copy backward (layernorm_bulk.cu); ALPRO_LN_BWD_BULK=0 (or another d) the
+    cp.async double-buffered one (one 12-warp block per SM); smaller M — or ALPRO_LN_BWD_ASYNC=0 — the register one."""
+    monkeypatch.setenv("ALPRO_LN_BWD_BULK", "1" if ln_path == "bulk" else "0")
+    monkeypatch.setenv("ALPRO_LN_FWD_BULK", "1" if ln_path == "bulk" else "0")
+    monkeypatch.setenv("ALPRO_LN_BWD_ASYNC", "0" if ln_path == "reg" else "1")
     ops = _ops()
     gen = g(2)
     x = torch.randn(M, d, device=DEV, generator=gen) * 2 + 0.3
@@ -168,6 +171,48 @@ def test_layernorm_fwd_bwd(d, eps, M, ln_async, monkeypatch):
         want16 = (base + xr.grad).clone()
         want16[torch.arange(M, device=DEV) % 7 == 0] = 0
         assert rel(dx16.float(), want16) < 1e-3
+
+
+@pytest.mark.parametrize("kind", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_layernorm_bwd_bulk_hooks(kind, accumulate):
+    """Bulk-copy LayerNorm backward (d = 768, M >= 4096) with every hook the TimeSformer backward uses: 16-bit / fp32
+    upstream gradient, overwrite / accumulate, stochastic-depth row scales on the 16-bit copy and on the column sums,
+    cls-row periods, bf16 output; checked against autograd."""
+    ops = _ops()
+    M, d, eps = 7 * 1571 + 3, 768, 1e-6
+    gen = g(21)
+    x = torch.randn(M, d, device=DEV, generator=gen) * 1.5 + 0.7
+    gamma = 1 + 0.1 * torch.randn(d, device=DEV, generator=gen)
+    beta = 0.1 * torch.randn(d, device=DEV, generator=gen)
+    st = torch.empty(2, M, device=DEV)
+    o16 = torch.empty(M, d, device=DEV, dtype=torch.float16)
+    ops.layernorm_fwd(x, gamma, beta, eps, out16=o16, mean=st[0], rstd=st[1])
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (d,), gr, br, eps)
+    dy = torch.randn(M, d, device=DEV, generator=gen).to(kind)
+    ref.backward(dy.float())
+    base = torch.randn(M, d, device=DEV, generator=gen)
+    dx = base.clone()
+    out_dt = torch.bfloat16 if kind == torch.bfloat16 else torch.float16
+    dx16 = torch.empty(M, d, device=DEV, dtype=out_dt)
+    rs16 = torch.rand(M, device=DEV, generator=gen) + 0.5
+    rsc = torch.rand(M, device=DEV, generator=gen) + 0.5
+    dg, db, cs = (torch.zeros(d, device=DEV) for _ in range(3))
+    ops.layernorm_bwd(dy, x, st[0], st[1], gamma, dx, accumulate, dx16=dx16, zero_period=1571, dgamma=dg, dbeta=db,
+                      param_scale=0.25, colsum=cs, colsum_zero_period=1571, dx16_row_scale=rs16, colsum_row_scale=rsc)
+    want = xr.grad + (base if accumulate else 0)
+    assert rel(dx, want) < 2e-5
+    assert rel(dg, 0.25 * gr.grad) < 1e-4 and rel(db, 0.25 * br.grad) < 1e-4
+    keep = (torch.arange(M, device=DEV) % 1571 != 0).float()[:, None]
+    assert rel(cs, 0.25 * (want * keep * rsc[:, None]).sum(0)) < 1e-4
+    assert rel(dx16.float(), want * keep * rs16[:, None]) < (1e-3 if out_dt == torch.float16 else 6e-3)
+    # column sums default to the dx16 row scale when no separate scale is given
+    cs2 = torch.zeros(d, device=DEV)
+    dx2 = base.clone()
+    ops.layernorm_bwd(dy, x, st[0], st[1], gamma, dx2, accumulate, dx16=dx16, colsum=cs2, dx16_row_scale=rs16)
+    assert rel(cs2, (want * rs16[:, None]).sum(0)) < 1e-4
 
 
 def test_colsum_cast():

@@ -69,7 +69,12 @@ ROT = 3   # 3 x (77..308 MB) per operand > 126 MB of L2
 rows = []
 
 
+ONLY = [t for t in os.environ.get("PROBE_ONLY", "").split(",") if t]   # substrings of case names; empty = all
+
+
 def add(name, fns, flop=0.0, bytes_=0.0):
+    if ONLY and not any(t in name for t in ONLY):
+        return
     us, j, w, mhz = measure(fns)
     rows.append((name, us, j, w, mhz, flop, bytes_))
     print(f"{name:44s} {us:9.1f} us {j * 1e3:9.2f} mJ {w:7.1f} W {mhz:5d} MHz", flush=True)
