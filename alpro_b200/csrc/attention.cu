@@ -1638,6 +1638,8 @@ int forward(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int B, i
 int backward(const void* qkv, int64_t ld_qkv, const void* dout, int64_t ld_dout, void* dqkv, int64_t ld_dqkv, int B,
              int N, int T, int heads, int fmt, float scale, cudaStream_t st);
 }  // namespace tattn
+int sattn_fwd_ps(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* cls_o, float* lse, int S, int nseq, int heads,
+                 int fmt, int seq_div, int stride, int64_t clip_rows, float scale, cudaStream_t st);
 }  // namespace alpro
 // The tcgen05 temporal-attention kernels are the default (T = 8: 0.085 / 0.104 ms vs 0.132 / 0.329 ms fwd / bwd at 32
 // clips); ALPRO_TATTN_TC=0 selects the CUDA-core kernels (read per call so tests can switch)
@@ -1840,6 +1842,12 @@ extern "C" int alpro_seq_attn_fwd(const void* qkv, int64_t ld_qkv, const float* 
   // at 256x12 sequences of 197). ALPRO_ATTN_TC=0 forces mma.sync, =1 forces tcgen05; read per call so tests can switch.
   const char* tc_env = getenv("ALPRO_ATTN_TC");
   if (tc_env && (tc_env[0] == '0' || tc_env[0] == '1') ? tc_env[0] == '1' : S >= 96) {
+    // persistent warp-specialised kernel for the strided two-tile layout without mask / dropout (sattn_ps.cu)
+    if (!mask && !p.drop_thr &&
+        sattn_fwd_ps(qkv, ld_qkv, o, ld_o, cls_o, lse, S, nseq, heads, fmt, seq_div, stride, clip_rows, scale, st) == ALPRO_OK) {
+      ALPRO_CHECK_LAUNCH("alpro_seq_attn_fwd(persistent)");
+      return 0;
+    }
     const size_t S32 = (S + 31) & ~31;
     const size_t smem_tc = 1024 + 128 * 128 + S32 * 128 * 2 + 2 * 16384 + (256 + 512) * sizeof(float) + 64;
     p.trace = trace_buffer(static_cast<size_t>(heads) * nseq, st);
