@@ -369,8 +369,8 @@ static bool map4(CUtensorMap* m, const uint16_t* mat, int64_t ld, int cols, int 
 int sattn_fwd_ps(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* cls_o, float* lse, int S, int nseq, int heads,
                  int fmt, int seq_div, int stride, int64_t clip_rows, float scale, cudaStream_t st) {
   using namespace sattn_ps;
-  const char* e = getenv("ALPRO_ATTN_PS");
-  if (!(e && e[0] == '1')) return ALPRO_ENOTSUP;
+  const char* e = getenv("ALPRO_ATTN_PS");   // default on; ALPRO_ATTN_PS=0 keeps the per-unit kernel (read per call)
+  if (e && e[0] == '0') return ALPRO_ENOTSUP;
   if (S <= 129 || S > 256 || (seq_div == 1 && stride == 1) || !encode_fn() || !lse) return ALPRO_ENOTSUP;
   const int d = heads * DH;
   if (!aligned16(qkv) || !aligned16(o) || (ld_qkv % 8) || (ld_o % 8) || 3 * d > ld_qkv || d > ld_o || nseq % seq_div ||

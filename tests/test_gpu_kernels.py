@@ -363,7 +363,9 @@ def test_temporal_attention(T, N, impl, monkeypatch):
 # forward: mma.sync (default) / tcgen05 (ALPRO_ATTN_TC=1); backward: mma.sync / tcgen05 (default for 96 <= S <= 240)
 # the tcgen05 kernels load their operand tiles by tensor-map (TMA) boxes (default) or by the per-thread cp.async gather
 # (ALPRO_ATTN_TMA=0)
-_ATTN_IMPLS = ["mma_sync", "tcgen05", "tcgen05_bwd", "tcgen05_gather", "tcgen05_bwd_gather"]
+# ALPRO_ATTN_PS=0: the per-unit tcgen05 forward instead of the persistent one (sattn_ps.cu, default for the strided
+# two-tile layout without mask / dropout)
+_ATTN_IMPLS = ["mma_sync", "tcgen05", "tcgen05_perunit", "tcgen05_bwd", "tcgen05_gather", "tcgen05_bwd_gather"]
 
 
 @pytest.fixture(params=_ATTN_IMPLS)
@@ -373,6 +375,7 @@ def attn_impl(request, monkeypatch):
     monkeypatch.setenv("ALPRO_ATTN_TC", "1" if request.param.startswith("tcgen05") and "bwd" not in request.param else "0")
     monkeypatch.setenv("ALPRO_ATTN_BWD_TC", "1" if request.param.startswith("tcgen05_bwd") else "0")
     monkeypatch.setenv("ALPRO_ATTN_TMA", "0" if request.param.endswith("gather") else "1")   # 1 = also for BERT rows
+    monkeypatch.setenv("ALPRO_ATTN_PS", "0" if request.param == "tcgen05_perunit" else "1")
     return request.param
 
 
@@ -435,6 +438,47 @@ def test_seq_attention_vit_layout(N, T, attn_impl):
     ops.seq_attn_bwd(qkv, None, lse, o, cls_o, do, dqkv, scratch, S, B * T, heads, T, T, Sc, 0.125)
     want.backward(do.float().view(B, Sc, d))
     assert rel(dqkv.float().view(B, Sc, 3 * d), x.grad) < 4e-3
+
+
+@pytest.mark.parametrize("B,T,N,heads,dt", [(2, 8, 196, 3, torch.float16), (1, 4, 160, 2, torch.float16),
+                                            (1, 2, 223, 2, torch.bfloat16), (3, 8, 196, 12, torch.bfloat16),
+                                            (1, 2, 129, 1, torch.float16)])
+def test_seq_attention_persistent_forward(B, T, N, heads, dt, monkeypatch):
+    """Persistent warp-specialised forward (sattn_ps.cu: operand ring, probabilities as a TMEM A operand, tensor-map
+    stores) against the per-unit tcgen05 kernel and a torch fp32 reference: patch rows, per-frame cls outputs, base-2
+    log-sum-exp in token order; the clip's cls row of o must stay untouched (cls_mean_fwd writes it later)."""
+    ops = _ops()
+    monkeypatch.setenv("ALPRO_ATTN_TC", "1")
+    d = heads * 64
+    Sc, S, nseq = 1 + N * T, 1 + N, B * T
+    gen = g(31)
+    qkv = torch.randn(B * Sc, 3 * d, device=DEV, generator=gen).to(dt)
+    outs = {}
+    for name, flag in (("unit", "0"), ("ps", "1")):
+        monkeypatch.setenv("ALPRO_ATTN_PS", flag)
+        o = torch.full((B * Sc, d), 7.0, device=DEV, dtype=dt)
+        cls_o = torch.full((nseq, d), 7.0, device=DEV, dtype=dt)
+        lse = torch.full((nseq, heads, S), 7.0, device=DEV)
+        ops.seq_attn_fwd(qkv, None, o, cls_o, lse, S, nseq, heads, T, T, Sc, 0.125)
+        torch.cuda.synchronize()
+        outs[name] = (o.float().view(B, Sc, d), cls_o.float(), lse)
+    x = qkv.float().view(B, Sc, 3 * d)
+    cls = x[:, :1].unsqueeze(1).expand(B, T, 1, 3 * d)
+    pat = x[:, 1:].view(B, N, T, 3 * d).permute(0, 2, 1, 3)
+    xs = torch.cat([cls, pat], 2).reshape(B * T, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    sc = (xs[0] @ xs[1].transpose(-1, -2)) * 0.125
+    ref = (torch.softmax(sc, -1) @ xs[2]).permute(0, 2, 1, 3).reshape(B, T, S, d)
+    want = ref[:, :, 1:].permute(0, 2, 1, 3).reshape(B, N * T, d)
+    tol = 3e-3 if dt == torch.float16 else 2e-2
+    for name in ("unit", "ps"):
+        o, c, lse = outs[name]
+        assert rel(o[:, 1:], want) < tol and rel(c.view(B, T, d), ref[:, :, 0]) < tol
+        assert bool((o[:, 0] == 7.0).all())
+        assert float((lse * math.log(2.0) - torch.logsumexp(sc, -1)).abs().max()) < 2e-3
+    # the two kernels round the same fp32 results: they may differ by one unit in the last place of a 16-bit output
+    ulp = 2.0 ** -10 if dt == torch.float16 else 2.0 ** -7
+    assert rel(outs["ps"][0][:, 1:], outs["unit"][0][:, 1:]) < 2 * ulp
+    assert float((outs["ps"][2] - outs["unit"][2]).abs().max()) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------------------------ heads
