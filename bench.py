@@ -304,18 +304,18 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     # board energy of the same step, measured after the timed region over a longer window (the NVML counter updates every
     # ~100 ms: 30+ steps keep the two end-point errors below a few percent); the window is bracketed by synchronize()
-    # EVERY rank runs these steps (a step contains the data-parallel collectives: a rank-0-only loop would leave the other
-    # ranks out of them and hang the job); rank 0 alone reads its board's counter.
+    # (A step contains the data-parallel collectives: anything that runs extra steps must run them on EVERY rank.)
+    # Single-GPU runs only: the scaling runs keep exactly the control flow that was validated at 8 GPUs.
     power = None
-    meter = EnergyMeter(D.local) if rank == 0 else None
-    n_en = max(args.steps, 30)
-    D.barrier()
-    en0 = meter.read() if meter is not None else None
-    for _ in range(n_en):
-        step(dev_batch)
-    D.barrier()
-    en1 = meter.read() if meter is not None else None
-    if meter is not None:
+    if world == 1:
+        meter = EnergyMeter(D.local)
+        n_en = max(args.steps, 30)
+        D.barrier()
+        en0 = meter.read()
+        for _ in range(n_en):
+            step(dev_batch)
+        D.barrier()
+        en1 = meter.read()
         power = meter.report(en0, en1, n_en, FLOP_PER_PAIR[kind] * B)
     e2e_step()
     ms_e2e = D.timed(e2e_step, args.steps)
