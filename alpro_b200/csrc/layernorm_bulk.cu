@@ -11,6 +11,9 @@
 //   * the fp32 arithmetic is packed (fma/mul/add.rn.f32x2 = FFMA2/FMUL2/FADD2, one issue slot per two lanes of a
 //     float4), x-hat and gamma*dy are kept in registers between the statistics pass and the output pass;
 //   * row-period tests (cls rows) are carried incrementally instead of a 64-bit modulo per row.
+// Reference semantics: nn.LayerNorm of the TimeSformer blocks (vit.py:140-154, eps 1e-6) and of BertSelfOutput /
+// BertOutput (xbert.py:349-360, 425-438, eps 1e-12): y = (x - mean) * rstd * gamma + beta with the biased variance;
+// backward dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.
 // Same contract as layernorm_bwd_async_kernel except for the 16-bit multiplier rows (BERT hidden-dropout masks), which
 // stay on the older kernel. ALPRO_LN_BWD_BULK=0 disables it (read per call).
 #include <cuda_fp16.h>

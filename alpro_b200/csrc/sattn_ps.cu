@@ -15,6 +15,9 @@
 //     in dead score columns; TMEM loads are issued one chunk ahead of the arithmetic;
 //   * O rows leave through a swizzled staging tile and ONE tensor-map store per tile.
 // Same outputs as the other forward kernels (o, per-sequence cls outputs, base-2 log-sum-exp in token order).
+// Reference semantics: Attention.forward, /root/reference/src/modeling/timesformer/vit.py:81-100, applied per frame to
+// the '(b t) (1 + h w) m' rearrangement of Block.forward's spatial branch (vit.py:165-196): softmax(q k^T * 64^-0.5) v
+// per head, with the clip's cls token prepended to every frame.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
